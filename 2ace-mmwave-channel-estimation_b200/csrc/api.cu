@@ -1,0 +1,795 @@
+// libtwoace C ABI (include/twoace.h): host orchestration of the sm_100a kernels.
+// No CPU fallback exists: every entry point launches CUDA kernels or fails with TWOACE_E_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/twoace.h"
+#include "solve_kernels.cuh"
+
+using namespace twoace;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct twoace_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = 0;
+  int chunk = 8192;
+  DevBuf arena, ws, taskbuf;
+  cd* cb_rm = nullptr;   // row-major codebook
+  int cb_rows = 0, cb_n = 0;
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),     \
+               __FILE__, __LINE__);                                                           \
+      ctx->err = buf_;                                                                        \
+      return TWOACE_E_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+#define FAIL(code, ...)                                  \
+  do {                                                   \
+    char buf_[512];                                      \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);            \
+    ctx->err = buf_;                                     \
+    return code;                                         \
+  } while (0)
+
+static int ensure(twoace_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 4096;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return 0;
+}
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = (off + 255) / 256 * 256;
+    off = o + bytes;
+    return o;
+  }
+};
+
+extern "C" void twoace_default_params(twoace_params* p) {
+  p->lambda = 0.0; p->r = 20; p->mu0 = 1e-3; p->rho = 1.03; p->cc_frac = 0.95;
+  p->tol_rel = 1e-4; p->tol_abs = 1e-8; p->maxiter = 500;
+}
+
+extern "C" int twoace_version(void) { return 100; }
+
+extern "C" int twoace_create(int device, twoace_ctx** out) {
+  if (!out) return TWOACE_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return TWOACE_E_CUDA;
+  }
+  twoace_ctx* ctx = new twoace_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete ctx;
+    return TWOACE_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->num_sms = prop.multiProcessorCount;
+  *out = ctx;
+  return TWOACE_OK;
+}
+
+extern "C" void twoace_destroy(twoace_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena.p) cudaFree(ctx->arena.p);
+  if (ctx->ws.p) cudaFree(ctx->ws.p);
+  if (ctx->taskbuf.p) cudaFree(ctx->taskbuf.p);
+  if (ctx->cb_rm) cudaFree(ctx->cb_rm);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* twoace_last_error(const twoace_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* twoace_stream(twoace_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int64_t twoace_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int twoace_synchronize(twoace_ctx* ctx) {
+  if (!ctx) return TWOACE_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int upload_tasks(twoace_ctx* ctx, const std::vector<T>& v, size_t& cursor, const T** dptr) {
+  // tasks are appended to ctx->taskbuf at `cursor`; the caller reserved enough space up front
+  size_t o = (cursor + 255) / 256 * 256;
+  size_t bytes = v.size() * sizeof(T);
+  if (o + bytes > ctx->taskbuf.cap) FAIL(TWOACE_E_NOMEM, "internal: task buffer too small");
+  CK(cudaMemcpyAsync((char*)ctx->taskbuf.p + o, v.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dptr = (const T*)((char*)ctx->taskbuf.p + o);
+  cursor = o + bytes;
+  return 0;
+}
+
+static int stage_grid(twoace_ctx* ctx, size_t smem, int ntasks, int* grid) {
+  int occ = 0;
+  CK(cudaFuncSetAttribute(admm_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, admm_stage_kernel, NT, smem));
+  if (occ < 1) FAIL(TWOACE_E_UNSUPPORTED, "stage kernel does not fit: %zu bytes of shared memory", smem);
+  *grid = std::max(1, std::min(ntasks, occ * ctx->num_sms));
+  return 0;
+}
+
+static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
+                        int tx, int rx, size_t& cursor) {
+  if (tasks.empty()) return 0;
+  StageDims dm;
+  dm.n = n; dm.tx = tx; dm.rx = rx; dm.maxm = 1; dm.maxr = 1; dm.dmax = 1;
+  bool nuc = false;
+  for (const StageTask& t : tasks) {
+    dm.maxm = std::max(dm.maxm, t.m);
+    dm.maxr = std::max(dm.maxr, t.r);
+    dm.dmax = std::max(dm.dmax, use_woodbury(t.m, n) ? t.m : n);
+    nuc = nuc || t.nuclear;
+  }
+  dm.ds = nuc ? std::max(tx, dm.maxr) : tx;
+  if (dm.ds > SMALL_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "tx (or r for the nuclear variant) > %d", SMALL_DMAX);
+  dm.ws_stride = (stage_ws_elems(dm) + 15) / 16 * 16;
+  const size_t smem = stage_smem_bytes(dm);
+  int grid = 0;
+  int rc = stage_grid(ctx, smem, (int)tasks.size(), &grid);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->ws, (size_t)grid * dm.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  const StageTask* dt = nullptr;
+  rc = upload_tasks(ctx, tasks, cursor, &dt);
+  if (rc) return rc;
+  admm_stage_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), prm, dm, (cd*)ctx->ws.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+static int launch_spectral(twoace_ctx* ctx, const std::vector<SpecTask>& tasks, int n, size_t& cursor) {
+  if (tasks.empty()) return 0;
+  SpecDims dm;
+  dm.n = n; dm.maxm = 1; dm.dmax = 1;
+  for (const SpecTask& t : tasks) {
+    dm.maxm = std::max(dm.maxm, t.m);
+    dm.dmax = std::max(dm.dmax, t.m <= n ? t.m : n);
+  }
+  dm.ws_stride = (spec_ws_elems(dm) + 15) / 16 * 16;
+  const size_t smem = spec_smem_bytes(dm);
+  int occ = 0;
+  CK(cudaFuncSetAttribute(spectral_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spectral_init_kernel, NT, smem));
+  if (occ < 1) FAIL(TWOACE_E_UNSUPPORTED, "spectral kernel does not fit: %zu bytes of shared memory", smem);
+  const int grid = std::max(1, std::min((int)tasks.size(), occ * ctx->num_sms));
+  int rc = ensure(ctx, ctx->ws, (size_t)grid * dm.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  const SpecTask* dt = nullptr;
+  rc = upload_tasks(ctx, tasks, cursor, &dt);
+  if (rc) return rc;
+  spectral_init_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), dm, (cd*)ctx->ws.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+static int launch_ortho(twoace_ctx* ctx, const std::vector<OrthoTask>& tasks, int n, size_t& cursor) {
+  if (tasks.empty()) return 0;
+  int rmax = 1;
+  for (const OrthoTask& t : tasks) rmax = std::max(rmax, t.r);
+  const size_t smem = ortho_smem_bytes(rmax);
+  CK(cudaFuncSetAttribute(ortho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::max(1, std::min((int)tasks.size(), 2 * ctx->num_sms));
+  const OrthoTask* dt = nullptr;
+  int rc = upload_tasks(ctx, tasks, cursor, &dt);
+  if (rc) return rc;
+  ortho_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), n, rmax);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// info words (twoace.h) from the control blocks and the stage bookkeeping
+__global__ void info_kernel(const InstCtl* ctl, const double* stage_words, int nstage, int nb, double* info,
+                            double* quality) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const InstCtl c = ctl[b];
+  if (quality) quality[b] = c.quality;
+  if (!info) return;
+  double* o = info + (size_t)b * TWOACE_INFO_WORDS;
+  const double* sw = stage_words + (size_t)b * nstage * STAGE_SCAL;
+  const double* rf = sw + (size_t)(nstage - 1) * STAGE_SCAL;
+  double tot = 0.0;
+  for (int s = 0; s < nstage; ++s) tot += sw[(size_t)s * STAGE_SCAL + SC_ITERS];
+  o[0] = c.quality; o[1] = c.similarity; o[2] = c.use_rank_one; o[3] = c.rolled_back;
+  o[4] = c.best_trial; o[5] = c.y_rows; o[6] = c.trial_r1_mask;
+  o[7] = c.trial_quality[0]; o[8] = c.trial_quality[1]; o[9] = c.trial_quality[2];
+  o[10] = c.max_quality; o[11] = rf[SC_ITERS]; o[12] = rf[SC_OPT_ITER]; o[13] = rf[SC_MU];
+  o[14] = rf[SC_BUMPS]; o[15] = tot;
+}
+
+static DevParams make_dev_params(const twoace_params& p) {
+  DevParams d;
+  d.mu0 = p.mu0; d.rho = p.rho; d.tol_rel = p.tol_rel; d.tol_abs = p.tol_abs; d.maxiter = p.maxiter;
+  d.need_dual = (p.tol_rel != 0.0 || p.tol_abs != 0.0) ? 1 : 0;
+  return d;
+}
+
+static int check_params(twoace_ctx* ctx, const twoace_params& p, int tx, int rx) {
+  if (p.lambda != 0.0) FAIL(TWOACE_E_UNSUPPORTED, "lambda != 0 is not supported (dead path in the reference)");
+  if (p.r < 1 || p.r > SMALL_DMAX) FAIL(TWOACE_E_INVALID, "r must be in [1,%d]", SMALL_DMAX);
+  if (!(p.cc_frac > 0.0 && p.cc_frac < 1.0)) FAIL(TWOACE_E_INVALID, "cc_frac must be in (0,1)");
+  if (p.maxiter < 1) FAIL(TWOACE_E_INVALID, "maxiter must be >= 1");
+  if (!(p.mu0 > 0.0) || !(p.rho > 0.0)) FAIL(TWOACE_E_INVALID, "mu0 and rho must be positive");
+  if (tx < 4 || tx > SMALL_DMAX || (tx % 4) != 0) FAIL(TWOACE_E_UNSUPPORTED, "tx must be a multiple of 4 in [4,%d]", SMALL_DMAX);
+  if (rx < 1) FAIL(TWOACE_E_INVALID, "rx must be >= 1");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+struct ChunkIn {
+  int variant, nb, tx, rx;
+  const int32_t* m;          // host
+  const cd* dA;              // device, dense mode (concat col-major) or nullptr
+  const int32_t* cb_rows;    // host, codebook mode or nullptr
+  double row_scale;
+  const double* dB;          // device
+  const int32_t* train_idx;  // host
+  twoace_params p;
+  cd* dX; cd* dY; double* dQ; double* dInfo; double* dStage;  // device outputs (dInfo/dStage may be null)
+};
+
+static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
+  const int nb = in.nb, n = in.tx * in.rx;
+  const bool multi = in.variant == TWOACE_V4_MULTI;
+  const int nuclear = in.variant == TWOACE_NUCLEAR ? 1 : 0;
+  const int T = multi ? 3 : 1;
+  const int nstage = 4 * T + 1;
+  const bool dense = in.dA != nullptr;
+
+  // ---- host bookkeeping (integer index work is bit-exact host code)
+  std::vector<size_t> a_off(nb + 1, 0), b_off(nb + 1, 0), tr_off(nb + 1, 0), te_off(nb + 1, 0);
+  std::vector<int> mtr(nb), mte(nb), rb(nb);
+  int maxr = 1;
+  for (int b = 0; b < nb; ++b) {
+    const int m = in.m[b];
+    if (m < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m);
+    mtr[b] = (int)std::floor((double)m * in.p.cc_frac);
+    mte[b] = m - mtr[b];
+    if (mtr[b] < 1 || mte[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: empty train or test split", b);
+    rb[b] = std::min(std::min((int)in.p.r, m), n);
+    maxr = std::max(maxr, rb[b]);
+    a_off[b + 1] = a_off[b] + (size_t)m * n;
+    b_off[b + 1] = b_off[b] + m;
+    tr_off[b + 1] = tr_off[b] + (size_t)T * mtr[b];
+    te_off[b + 1] = te_off[b] + (size_t)T * mte[b];
+  }
+  // index lists: trainB/testB index the instance's B (and dense A rows); trainA/testA index the
+  // matrix the AView points at (== trainB/testB in dense mode, codebook rows otherwise)
+  std::vector<int32_t> trainB(tr_off[nb]), testB(te_off[nb]), trainA, testA, fullA;
+  if (!dense) { trainA.resize(tr_off[nb]); testA.resize(te_off[nb]); fullA.resize(b_off[nb]); }
+  std::vector<char> mark;
+  for (int b = 0; b < nb; ++b) {
+    const int m = in.m[b];
+    for (int t = 0; t < T; ++t) {
+      const int32_t* tr = in.train_idx + tr_off[b] + (size_t)t * mtr[b];
+      mark.assign(m, 0);
+      for (int i = 0; i < mtr[b]; ++i) {
+        const int v = tr[i];
+        if (v < 0 || v >= m || mark[v]) FAIL(TWOACE_E_INVALID, "instance %d trial %d: train_idx must be unique and in [0,m)", b, t);
+        mark[v] = 1;
+        trainB[tr_off[b] + (size_t)t * mtr[b] + i] = v;
+      }
+      int k = 0;
+      for (int v = 0; v < m; ++v)
+        if (!mark[v]) testB[te_off[b] + (size_t)t * mte[b] + k++] = v;   // setdiff(1:m, train): ascending
+    }
+    if (!dense) {
+      const int32_t* rows = in.cb_rows + b_off[b];
+      for (int i = 0; i < m; ++i) {
+        if (rows[i] < 0 || rows[i] >= ctx->cb_rows) FAIL(TWOACE_E_INVALID, "instance %d: codebook row %d out of range", b, rows[i]);
+        fullA[b_off[b] + i] = rows[i];
+      }
+      for (size_t i = 0; i < (size_t)T * mtr[b]; ++i) trainA[tr_off[b] + i] = rows[trainB[tr_off[b] + i]];
+      for (size_t i = 0; i < (size_t)T * mte[b]; ++i) testA[te_off[b] + i] = rows[testB[te_off[b] + i]];
+    }
+  }
+
+  // ---- device arena layout
+  Bump bp;
+  const size_t o_trainB = bp.take(trainB.size() * 4), o_testB = bp.take(testB.size() * 4);
+  const size_t o_trainA = dense ? o_trainB : bp.take(trainA.size() * 4);
+  const size_t o_testA = dense ? o_testB : bp.take(testA.size() * 4);
+  const size_t o_fullA = dense ? 0 : bp.take(fullA.size() * 4);
+  const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
+  const size_t o_Arm = dense ? bp.take(a_off[nb] * sizeof(cd)) : 0;
+  const size_t xstride = (size_t)n * maxr;
+  const size_t o_Xs = bp.take((size_t)nb * xstride * sizeof(cd));
+  const size_t o_Xa = bp.take((size_t)nb * xstride * sizeof(cd));
+  const size_t o_xb = bp.take((size_t)nb * n * sizeof(cd));
+  const size_t o_xmax = bp.take((size_t)nb * n * sizeof(cd));
+  const size_t o_xr = bp.take((size_t)nb * n * sizeof(cd));
+  const size_t o_yb = bp.take(b_off[nb] * sizeof(cd));
+  const size_t o_ymax = bp.take(b_off[nb] * sizeof(cd));
+  const size_t o_yr = bp.take(b_off[nb] * sizeof(cd));
+  const size_t o_sw = bp.take((size_t)nb * nstage * STAGE_SCAL * sizeof(double));
+  int rc = ensure(ctx, ctx->arena, bp.off + 256);
+  if (rc) return rc;
+  char* base = (char*)ctx->arena.p;
+  int* d_trainB = (int*)(base + o_trainB); int* d_testB = (int*)(base + o_testB);
+  int* d_trainA = (int*)(base + o_trainA); int* d_testA = (int*)(base + o_testA);
+  int* d_fullA = dense ? nullptr : (int*)(base + o_fullA);
+  InstCtl* d_ctl = (InstCtl*)(base + o_ctl);
+  cd* d_Arm = dense ? (cd*)(base + o_Arm) : nullptr;
+  cd* d_Xs = (cd*)(base + o_Xs); cd* d_Xa = (cd*)(base + o_Xa);
+  cd* d_xb = (cd*)(base + o_xb); cd* d_xmax = (cd*)(base + o_xmax); cd* d_xr = (cd*)(base + o_xr);
+  cd* d_yb = (cd*)(base + o_yb); cd* d_ymax = (cd*)(base + o_ymax); cd* d_yr = (cd*)(base + o_yr);
+  double* d_sw = (double*)(base + o_sw);
+
+  CK(cudaMemcpyAsync(d_trainB, trainB.data(), trainB.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_testB, testB.data(), testB.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!dense) {
+    CK(cudaMemcpyAsync(d_trainA, trainA.data(), trainA.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_testA, testA.data(), testA.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_fullA, fullA.data(), fullA.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemsetAsync(d_sw, 0, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), ctx->stream));
+
+  // task buffer: generous upper bound for all task arrays of this chunk
+  const size_t task_bytes = (size_t)nb * (sizeof(PrepTask) + T * (sizeof(SpecTask) + 4 * sizeof(StageTask) +
+                            2 * sizeof(OrthoTask) + 2 * sizeof(QualTask)) + sizeof(StageTask) + sizeof(FinalTask)) +
+                            256 * (8 * T + 8);
+  rc = ensure(ctx, ctx->taskbuf, task_bytes);
+  if (rc) return rc;
+  size_t cursor = 0;
+  const DevParams prm = make_dev_params(in.p);
+  const cd* Abase_all = dense ? d_Arm : ctx->cb_rm;
+
+  // ---- pre-processing
+  {
+    std::vector<PrepTask> pt(nb);
+    for (int b = 0; b < nb; ++b) {
+      PrepTask& t = pt[b];
+      t.A_cm = dense ? in.dA + a_off[b] : nullptr;
+      t.A_rm = dense ? d_Arm + a_off[b] : nullptr;
+      t.cb = ctx->cb_rm; t.cbrows = dense ? nullptr : d_fullA + b_off[b];
+      t.row_scale = in.row_scale; t.B = in.dB + b_off[b]; t.m = in.m[b]; t.ctl = d_ctl + b;
+    }
+    const PrepTask* dt = nullptr;
+    rc = upload_tasks(ctx, pt, cursor, &dt);
+    if (rc) return rc;
+    prep_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dt, nb, n, in.p.tol_abs);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    fill_nan_kernel<<<std::min(4 * ctx->num_sms, (int)(((size_t)nb * n + 255) / 256)), 256, 0, ctx->stream>>>(d_xmax, (size_t)nb * n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  auto aview = [&](int b, const int* rows) {
+    AView v;
+    v.base = dense ? d_Arm + a_off[b] : Abase_all;
+    v.rows = rows;
+    v.scale = &d_ctl[b].a_scale;
+    return v;
+  };
+
+  for (int t = 0; t < T; ++t) {
+    // ---- spectral initialisation on the training rows
+    {
+      std::vector<SpecTask> st(nb);
+      for (int b = 0; b < nb; ++b) {
+        SpecTask& s = st[b];
+        s.A = aview(b, d_trainA + tr_off[b] + (size_t)t * mtr[b]);
+        s.B = in.dB + b_off[b]; s.brows = d_trainB + tr_off[b] + (size_t)t * mtr[b];
+        s.bscale = &d_ctl[b].b_scale; s.m = mtr[b]; s.r = rb[b];
+        s.Xs = d_Xs + (size_t)b * xstride; s.sweeps = nullptr;
+      }
+      rc = launch_spectral(ctx, st, n, cursor);
+      if (rc) return rc;
+    }
+    for (int pass = 0; pass < 2; ++pass) {   // pass 1 = rank-one rerun, masked by ctl.need_r1
+      std::vector<StageTask> sa(nb), sb(nb);
+      std::vector<OrthoTask> ot(nb);
+      std::vector<QualTask> qt(nb);
+      for (int b = 0; b < nb; ++b) {
+        StageTask& a = sa[b];
+        a.A = aview(b, d_trainA + tr_off[b] + (size_t)t * mtr[b]);
+        a.B = in.dB + b_off[b]; a.brows = d_trainB + tr_off[b] + (size_t)t * mtr[b];
+        a.bscale = &d_ctl[b].b_scale; a.m = mtr[b]; a.r = rb[b];
+        a.X0 = d_Xs + (size_t)b * xstride; a.Xout = d_Xa + (size_t)b * xstride; a.Yout = nullptr;
+        a.sbr = 1; a.rank_one = pass; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
+        a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
+        a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
+        StageTask& s2 = sb[b];
+        s2 = a;
+        s2.X0 = d_Xa + (size_t)b * xstride; s2.Xout = d_xb + (size_t)b * n; s2.Yout = d_yb + b_off[b];
+        s2.sbr = 0;
+        s2.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass + 1) * STAGE_SCAL;
+        OrthoTask& o = ot[b];
+        o.X = d_Xa + (size_t)b * xstride; o.r = rb[b]; o.active = a.active; o.active_expect = 1;
+        QualTask& q = qt[b];
+        q.A = aview(b, d_testA + te_off[b] + (size_t)t * mte[b]);
+        q.B = in.dB + b_off[b]; q.brows = d_testB + te_off[b] + (size_t)t * mte[b];
+        q.bscale = &d_ctl[b].b_scale; q.mte = mte[b]; q.x = d_xb + (size_t)b * n; q.y = d_yb + b_off[b];
+        q.mtr = mtr[b]; q.xmax = d_xmax + (size_t)b * n; q.ymax = d_ymax + b_off[b];
+        q.ctl = d_ctl + b; q.trial = t; q.pass = pass; q.multi = multi ? 1 : 0;
+      }
+      rc = launch_stage(ctx, sa, prm, n, in.tx, in.rx, cursor);
+      if (rc) return rc;
+      rc = launch_ortho(ctx, ot, n, cursor);
+      if (rc) return rc;
+      rc = launch_stage(ctx, sb, prm, n, in.tx, in.rx, cursor);
+      if (rc) return rc;
+      const QualTask* dq = nullptr;
+      rc = upload_tasks(ctx, qt, cursor, &dq);
+      if (rc) return rc;
+      quality_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dq, nb, n);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+  }
+  // ---- refine on all rows (:68-80), then roll-back / rescale (:72-86)
+  {
+    std::vector<StageTask> sr(nb);
+    std::vector<FinalTask> ft(nb);
+    for (int b = 0; b < nb; ++b) {
+      StageTask& a = sr[b];
+      a.A = aview(b, dense ? nullptr : d_fullA + b_off[b]);
+      a.B = in.dB + b_off[b]; a.brows = nullptr; a.bscale = &d_ctl[b].b_scale;
+      a.m = in.m[b]; a.r = 1; a.X0 = d_xmax + (size_t)b * n; a.Xout = d_xr + (size_t)b * n; a.Yout = d_yr + b_off[b];
+      a.sbr = 1; a.rank_one = 0; a.nuclear = nuclear; a.rank_one_ptr = &d_ctl[b].use_rank_one;
+      a.active = nullptr; a.active_expect = 1;
+      a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
+      FinalTask& f = ft[b];
+      f.x0 = d_xmax + (size_t)b * n; f.y0 = d_ymax + b_off[b]; f.xr = d_xr + (size_t)b * n; f.yr = d_yr + b_off[b];
+      f.m = in.m[b]; f.mtr = mtr[b]; f.Xout = in.dX + (size_t)b * n; f.Yout = in.dY + b_off[b];
+      f.quality_out = in.dQ + b; f.ctl = d_ctl + b;
+    }
+    rc = launch_stage(ctx, sr, prm, n, in.tx, in.rx, cursor);
+    if (rc) return rc;
+    const FinalTask* df = nullptr;
+    rc = upload_tasks(ctx, ft, cursor, &df);
+    if (rc) return rc;
+    final_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(df, nb, n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (in.dInfo) {
+    info_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(d_ctl, d_sw, nstage, nb, in.dInfo, nullptr);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (in.dStage)
+    CK(cudaMemcpyAsync(in.dStage, d_sw, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+// Host-pointer staging helper: device mirrors of inputs/outputs for one call.
+struct Staging {
+  std::vector<void*> owned;
+  ~Staging() { for (void* p : owned) cudaFree(p); }
+};
+
+static int dev_in(twoace_ctx* ctx, Staging& st, int mem, const void* src, size_t bytes, const void** dst) {
+  if (mem == TWOACE_MEM_DEVICE || bytes == 0) { *dst = src; return 0; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for input staging failed", bytes); }
+  st.owned.push_back(p);
+  CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dst = p;
+  return 0;
+}
+static int dev_out(twoace_ctx* ctx, Staging& st, int mem, void* host, size_t bytes, void** dst) {
+  if (host == nullptr) { *dst = nullptr; return 0; }
+  if (mem == TWOACE_MEM_DEVICE) { *dst = host; return 0; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for output staging failed", bytes); }
+  st.owned.push_back(p);
+  *dst = p;
+  return 0;
+}
+static int host_back(twoace_ctx* ctx, int mem, void* host, const void* dev, size_t bytes) {
+  if (mem == TWOACE_MEM_DEVICE || host == nullptr || bytes == 0) return 0;
+  CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx, const int32_t* m,
+                        const double* A, const int32_t* cb_rows, double row_scale, const double* B,
+                        const int32_t* train_idx, const twoace_params* params, double* X, double* Y,
+                        double* quality, double* info, double* stage_words) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (variant < TWOACE_V4 || variant > TWOACE_NUCLEAR) FAIL(TWOACE_E_INVALID, "unknown variant %d", variant);
+  if (nb < 0 || !m || !B || !train_idx || !X || !Y || !quality) FAIL(TWOACE_E_INVALID, "null argument");
+  if (!A && !cb_rows) FAIL(TWOACE_E_INVALID, "neither dense A nor codebook rows given");
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  twoace_params p;
+  if (params) p = *params; else twoace_default_params(&p);
+  int rc = check_params(ctx, p, tx, rx);
+  if (rc) return rc;
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n = tx * rx;
+  if (!A) {
+    if (!ctx->cb_rm) FAIL(TWOACE_E_INVALID, "no codebook registered (twoace_set_codebook)");
+    if (ctx->cb_n != n) FAIL(TWOACE_E_INVALID, "codebook has n = %d, call has tx*rx = %d", ctx->cb_n, n);
+  }
+  const int T = variant == TWOACE_V4_MULTI ? 3 : 1;
+  const int nstage = 4 * T + 1;
+  size_t sum_m = 0, sum_tr = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (m[b] < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m[b]);
+    sum_m += m[b];
+    sum_tr += (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+  }
+  Staging st;
+  const void *dA = nullptr, *dB = nullptr;
+  void *dX = nullptr, *dY = nullptr, *dQ = nullptr, *dI = nullptr, *dS = nullptr;
+  if (A) { rc = dev_in(ctx, st, mem, A, sum_m * n * sizeof(cd), &dA); if (rc) return rc; }
+  rc = dev_in(ctx, st, mem, B, sum_m * sizeof(double), &dB); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, X, (size_t)nb * n * sizeof(cd), &dX); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, Y, sum_m * sizeof(cd), &dY); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, quality, (size_t)nb * sizeof(double), &dQ); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, info, (size_t)nb * TWOACE_INFO_WORDS * sizeof(double), &dI); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, stage_words, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), &dS); if (rc) return rc;
+
+  size_t ao = 0, bo = 0, to = 0;
+  for (int b0 = 0; b0 < nb; b0 += ctx->chunk) {
+    const int cnt = std::min(ctx->chunk, nb - b0);
+    ChunkIn in;
+    in.variant = variant; in.nb = cnt; in.tx = tx; in.rx = rx; in.m = m + b0;
+    in.dA = A ? (const cd*)dA + ao : nullptr;
+    in.cb_rows = cb_rows ? cb_rows + bo : nullptr;
+    in.row_scale = row_scale;
+    in.dB = (const double*)dB + bo; in.train_idx = train_idx + to; in.p = p;
+    in.dX = (cd*)dX + (size_t)b0 * n; in.dY = (cd*)dY + bo; in.dQ = (double*)dQ + b0;
+    in.dInfo = dI ? (double*)dI + (size_t)b0 * TWOACE_INFO_WORDS : nullptr;
+    in.dStage = dS ? (double*)dS + (size_t)b0 * nstage * STAGE_SCAL : nullptr;
+    rc = solve_chunk(ctx, in);
+    if (rc) return rc;
+    for (int b = b0; b < b0 + cnt; ++b) {
+      ao += (size_t)m[b] * n; bo += m[b];
+      to += (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+    }
+  }
+  rc = host_back(ctx, mem, X, dX, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, Y, dY, sum_m * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, quality, dQ, (size_t)nb * sizeof(double)); if (rc) return rc;
+  rc = host_back(ctx, mem, info, dI, (size_t)nb * TWOACE_INFO_WORDS * sizeof(double)); if (rc) return rc;
+  rc = host_back(ctx, mem, stage_words, dS, (size_t)nb * nstage * STAGE_SCAL * sizeof(double)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_solve_batch(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx,
+                                  const int32_t* m, const double* A, const double* B, const int32_t* train_idx,
+                                  const twoace_params* params, double* X, double* Y, double* quality,
+                                  double* info, double* stage_words) {
+  if (ctx && !A) { ctx->err = "A is null"; return TWOACE_E_INVALID; }
+  return solve_common(ctx, variant, mem, nb, tx, rx, m, A, nullptr, 1.0, B, train_idx, params, X, Y, quality, info, stage_words);
+}
+
+extern "C" int twoace_solve_batch_codebook(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx,
+                                           const int32_t* m, const int32_t* cb_rows, double row_scale,
+                                           const double* B, const int32_t* train_idx, const twoace_params* params,
+                                           double* X, double* Y, double* quality, double* info, double* stage_words) {
+  if (ctx && !cb_rows) { ctx->err = "cb_rows is null"; return TWOACE_E_INVALID; }
+  return solve_common(ctx, variant, mem, nb, tx, rx, m, nullptr, cb_rows, row_scale, B, train_idx, params, X, Y, quality, info, stage_words);
+}
+
+__global__ void transpose_cm_to_rm(const cd* __restrict__ src, cd* __restrict__ dst, int rows, int n) {
+  // src: rows x n column-major; dst: rows x n row-major
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)rows * n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % n);
+    const size_t i = idx / n;
+    dst[idx] = src[i + (size_t)rows * k];
+  }
+}
+
+extern "C" int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, const double* cb) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (rows < 1 || n < 1 || !cb) FAIL(TWOACE_E_INVALID, "bad codebook arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->cb_rm) { CK(cudaFree(ctx->cb_rm)); ctx->cb_rm = nullptr; }
+  const size_t bytes = (size_t)rows * n * sizeof(cd);
+  CK(cudaMalloc((void**)&ctx->cb_rm, bytes));
+  Staging st;
+  const void* dsrc = nullptr;
+  int rc = dev_in(ctx, st, mem, cb, bytes, &dsrc);
+  if (rc) return rc;
+  transpose_cm_to_rm<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>((const cd*)dsrc, ctx->cb_rm, rows, n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cb_rows = rows; ctx->cb_n = n;
+  return TWOACE_OK;
+}
+
+// Fill the constant scalars the stand-alone stage / spectral entry points need (scale = 1).
+__global__ void set_ones_kernel(double* p, int cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) p[i] = 1.0;
+}
+
+extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const int32_t* m,
+                                       const double* A, const double* B, int r, const double* X0,
+                                       int scale_by_row, int use_rank_one, int nuclear,
+                                       const twoace_params* params, double* X, double* Y, double* state,
+                                       double* words) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !m || !A || !B || !X0 || !X || !Y) FAIL(TWOACE_E_INVALID, "null argument");
+  twoace_params p;
+  if (params) p = *params; else twoace_default_params(&p);
+  p.r = std::min(std::max(r, 1), SMALL_DMAX);
+  int rc = check_params(ctx, p, tx, rx);
+  if (rc) return rc;
+  if (r < 1 || r > SMALL_DMAX) FAIL(TWOACE_E_INVALID, "r must be in [1,%d]", SMALL_DMAX);
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n = tx * rx;
+  const int rout = scale_by_row ? r : 1;
+  std::vector<size_t> a_off(nb + 1, 0), b_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) {
+    if (m[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: m < 1", b);
+    a_off[b + 1] = a_off[b] + (size_t)m[b] * n;
+    b_off[b + 1] = b_off[b] + m[b];
+  }
+  const size_t sum_m = b_off[nb];
+  std::vector<size_t> st_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) st_off[b + 1] = st_off[b] + 3 * (size_t)n * r + 2 * (size_t)m[b] * r;
+  Staging st;
+  const void *dA, *dB, *dX0;
+  void *dX, *dY, *dSt, *dW;
+  rc = dev_in(ctx, st, mem, A, a_off[nb] * sizeof(cd), &dA); if (rc) return rc;
+  rc = dev_in(ctx, st, mem, B, sum_m * sizeof(double), &dB); if (rc) return rc;
+  rc = dev_in(ctx, st, mem, X0, (size_t)nb * n * r * sizeof(cd), &dX0); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, X, (size_t)nb * n * rout * sizeof(cd), &dX); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, Y, sum_m * rout * sizeof(cd), &dY); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, state, st_off[nb] * sizeof(cd), &dSt); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, words, (size_t)nb * STAGE_SCAL * sizeof(double), &dW); if (rc) return rc;
+  // arena: row-major A + the unit scalar
+  Bump bp;
+  const size_t o_Arm = bp.take(a_off[nb] * sizeof(cd)), o_one = bp.take(sizeof(double));
+  const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
+  rc = ensure(ctx, ctx->arena, bp.off + 256); if (rc) return rc;
+  char* base = (char*)ctx->arena.p;
+  cd* d_Arm = (cd*)(base + o_Arm);
+  double* d_one = (double*)(base + o_one);
+  InstCtl* d_ctl = (InstCtl*)(base + o_ctl);
+  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(StageTask)) + 4096); if (rc) return rc;
+  size_t cursor = 0;
+  set_ones_kernel<<<1, 32, 0, ctx->stream>>>(d_one, 1);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  {
+    std::vector<PrepTask> pt(nb);
+    for (int b = 0; b < nb; ++b) {
+      PrepTask& t = pt[b];
+      t.A_cm = (const cd*)dA + a_off[b]; t.A_rm = d_Arm + a_off[b]; t.cb = nullptr; t.cbrows = nullptr;
+      t.row_scale = 1.0; t.B = (const double*)dB + b_off[b]; t.m = m[b]; t.ctl = d_ctl + b;
+    }
+    const PrepTask* dt = nullptr;
+    rc = upload_tasks(ctx, pt, cursor, &dt); if (rc) return rc;
+    prep_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dt, nb, n, 0.0);   // only the transpose is used
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  std::vector<StageTask> tasks(nb);
+  for (int b = 0; b < nb; ++b) {
+    StageTask& a = tasks[b];
+    a.A.base = d_Arm + a_off[b]; a.A.rows = nullptr; a.A.scale = d_one;
+    a.B = (const double*)dB + b_off[b]; a.brows = nullptr; a.bscale = d_one;
+    a.m = m[b]; a.r = r; a.X0 = (const cd*)dX0 + (size_t)b * n * r;
+    a.Xout = (cd*)dX + (size_t)b * n * rout; a.Yout = (cd*)dY + b_off[b] * rout;
+    a.sbr = scale_by_row ? 1 : 0; a.rank_one = use_rank_one ? 1 : 0; a.nuclear = nuclear ? 1 : 0;
+    a.rank_one_ptr = nullptr; a.active = nullptr; a.active_expect = 1;
+    a.scal = dW ? (double*)dW + (size_t)b * STAGE_SCAL : nullptr;
+    a.state = dSt ? (cd*)dSt + st_off[b] : nullptr;
+  }
+  rc = launch_stage(ctx, tasks, make_dev_params(p), n, tx, rx, cursor); if (rc) return rc;
+  rc = host_back(ctx, mem, X, dX, (size_t)nb * n * rout * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, Y, dY, sum_m * rout * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, state, dSt, st_off[nb] * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, words, dW, (size_t)nb * STAGE_SCAL * sizeof(double)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m,
+                                          const double* A, const double* B, int r, double* Xs) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !m || !A || !B || !Xs || n < 1 || r < 1) FAIL(TWOACE_E_INVALID, "bad argument");
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<size_t> a_off(nb + 1, 0), b_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) {
+    if (m[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: m < 1", b);
+    a_off[b + 1] = a_off[b] + (size_t)m[b] * n;
+    b_off[b + 1] = b_off[b] + m[b];
+  }
+  Staging st;
+  const void *dA, *dB;
+  void* dXs;
+  int rc = dev_in(ctx, st, mem, A, a_off[nb] * sizeof(cd), &dA); if (rc) return rc;
+  rc = dev_in(ctx, st, mem, B, b_off[nb] * sizeof(double), &dB); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, Xs, (size_t)nb * n * r * sizeof(cd), &dXs); if (rc) return rc;
+  Bump bp;
+  const size_t o_Arm = bp.take(a_off[nb] * sizeof(cd)), o_one = bp.take(sizeof(double));
+  const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
+  rc = ensure(ctx, ctx->arena, bp.off + 256); if (rc) return rc;
+  char* base = (char*)ctx->arena.p;
+  cd* d_Arm = (cd*)(base + o_Arm);
+  double* d_one = (double*)(base + o_one);
+  InstCtl* d_ctl = (InstCtl*)(base + o_ctl);
+  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(SpecTask)) + 4096); if (rc) return rc;
+  size_t cursor = 0;
+  set_ones_kernel<<<1, 32, 0, ctx->stream>>>(d_one, 1);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  {
+    std::vector<PrepTask> pt(nb);
+    for (int b = 0; b < nb; ++b) {
+      PrepTask& t = pt[b];
+      t.A_cm = (const cd*)dA + a_off[b]; t.A_rm = d_Arm + a_off[b]; t.cb = nullptr; t.cbrows = nullptr;
+      t.row_scale = 1.0; t.B = (const double*)dB + b_off[b]; t.m = m[b]; t.ctl = d_ctl + b;
+    }
+    const PrepTask* dt = nullptr;
+    rc = upload_tasks(ctx, pt, cursor, &dt); if (rc) return rc;
+    prep_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dt, nb, n, 0.0);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  std::vector<SpecTask> tasks(nb);
+  for (int b = 0; b < nb; ++b) {
+    SpecTask& s = tasks[b];
+    s.A.base = d_Arm + a_off[b]; s.A.rows = nullptr; s.A.scale = d_one;
+    s.B = (const double*)dB + b_off[b]; s.brows = nullptr; s.bscale = d_one;
+    s.m = m[b]; s.r = std::min(r, std::min(m[b], n)); s.Xs = (cd*)dXs + (size_t)b * n * r; s.sweeps = nullptr;
+  }
+  if (true) {   // columns beyond min(r, m, n) stay zero
+    CK(cudaMemsetAsync(dXs, 0, (size_t)nb * n * r * sizeof(cd), ctx->stream));
+  }
+  rc = launch_spectral(ctx, tasks, n, cursor); if (rc) return rc;
+  rc = host_back(ctx, mem, Xs, dXs, (size_t)nb * n * r * sizeof(cd)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}

@@ -1,0 +1,439 @@
+// Setup / control kernels around the InferADMM stage kernel: pre-processing, spectral
+// initialisation, column orthonormalisation, held-out quality, best-trial tracking, refine
+// roll-back and output scaling.  One CTA per instance; every data-dependent decision of
+//   inferLowRankV4.m:11-88 / inferLowRankV4_multi.m:18-108
+// is taken on the device and recorded in the per-instance InstCtl words, so the host issues a
+// fixed launch sequence with no round trips.
+#pragma once
+#include "admm_stage.cuh"
+
+namespace twoace {
+
+// Per-instance control block (device resident).
+struct InstCtl {
+  double a_scale;      // 1 / A_norm                                   (:20-23,:30)
+  double b_scale;      // 1 / B_norm                                   (:25-28,:31)
+  double out_scale;    // B_norm / A_norm                              (:85-86)
+  double quality;      // quality of the current (last) trial          (:54,:62)
+  double max_quality;  // _multi.m:40,79-83
+  double similarity;   // :72
+  int need_r1;         // 1 while the rank-one rerun of the current trial is pending (:59-63)
+  int use_rank_one;    // use_rank_one of the last trial (feeds the refine stage, H6)
+  int best_trial;
+  int rolled_back;
+  int y_rows;          // rows of the returned Y (m, or m_train after a roll-back)
+  int trial_r1_mask;   // bit t set when trial t used the rank-one profile
+  double trial_quality[3];
+};
+
+// ---- pre-processing ----------------------------------------------------------------------
+struct PrepTask {
+  const cd* A_cm;      // dense mode: m x n column-major input (device); nullptr in codebook mode
+  cd* A_rm;            // dense mode: row-major copy written here
+  const cd* cb;        // codebook mode: row-major codebook
+  const int* cbrows;   // codebook mode: row ids [m]
+  double row_scale;    // codebook mode: A = row_scale * cb[rows]
+  const double* B;     // [m]
+  int m;
+  InstCtl* ctl;
+};
+
+__global__ void __launch_bounds__(NT) prep_kernel(const PrepTask* __restrict__ tasks, int ntasks, int n,
+                                                  double tol_abs) {
+  __shared__ double red[16 * NW];
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const PrepTask tk = tasks[t];
+    const int tid = threadIdx.x, m = tk.m;
+    double v[2] = {0.0, 0.0};
+    if (tk.A_cm) {
+      for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {   // idx over the row-major output
+        const int k = (int)(idx % n), i = (int)(idx / n);
+        const cd a = tk.A_cm[i + (size_t)m * k];
+        tk.A_rm[idx] = a;
+        v[0] += cabs2(a);
+      }
+    } else {
+      for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {
+        const int k = (int)(idx % n), i = (int)(idx / n);
+        v[0] += cabs2(tk.cb[(size_t)tk.cbrows[i] * n + k]);
+      }
+      v[0] *= tk.row_scale * tk.row_scale;
+    }
+    for (int i = tid; i < m; i += NT) v[1] += tk.B[i] * tk.B[i];
+    block_sum<2>(v, red);
+    if (tid == 0) {
+      double A_norm = sqrt(v[0]) / sqrt((double)m);
+      if (A_norm < tol_abs) A_norm = 1.0;
+      double B_norm = sqrt(v[1]);
+      if (B_norm < tol_abs) B_norm = 1.0;
+      InstCtl c;
+      c.a_scale = (tk.A_cm ? 1.0 : tk.row_scale) / A_norm;
+      c.b_scale = 1.0 / B_norm;
+      c.out_scale = B_norm / A_norm;
+      c.quality = NAN; c.max_quality = -1.0; c.similarity = NAN;
+      c.need_r1 = 0; c.use_rank_one = 0; c.best_trial = -1; c.rolled_back = 0; c.y_rows = m;
+      c.trial_r1_mask = 0;
+      c.trial_quality[0] = c.trial_quality[1] = c.trial_quality[2] = NAN;
+      *tk.ctl = c;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- spectral initialisation (inferLowRankV4.m:540-553) -------------------------------------
+// eig(As'As) (n x n) is replaced by the m x m Gram problem when m <= n:
+//   As = W S V'  =>  As As' = W S^2 W',  V(:,j) sqrt(s2_j) = As' W(:,j).
+struct SpecTask {
+  AView A;             // training rows
+  const double* B; const int* brows; const double* bscale;
+  int m, r;
+  cd* Xs;              // n x r out
+  int* sweeps;         // optional
+};
+
+struct SpecDims { int n, maxm, dmax; size_t ws_stride; };
+
+__host__ __device__ inline size_t spec_ws_elems(const SpecDims& d) {
+  return (size_t)d.maxm * d.n + 2 * (size_t)d.dmax * d.dmax;
+}
+__host__ __device__ inline size_t spec_smem_bytes(const SpecDims& d) {
+  size_t b = 0;
+  b += ((size_t)d.maxm * (2 * sizeof(double) + sizeof(int)) + 15) / 16 * 16;   // w, rows
+  b += (size_t)QT * RCH * sizeof(cd) + (size_t)NT * RCH * sizeof(cd);          // tile, ksred
+  b += (size_t)(d.dmax / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));           // jacobi
+  b += (size_t)d.dmax * (sizeof(double) + sizeof(int));                        // s2, order
+  b += 16 * NW * sizeof(double) + 64;
+  return b + 64;
+}
+
+__global__ void __launch_bounds__(NT, 2)
+spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm, cd* wsbase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  double* wrow = (double*)p;  p += (size_t)dm.maxm * sizeof(double);
+  double* Bs = (double*)p;    p += (size_t)dm.maxm * sizeof(double);
+  int* rows_s = (int*)p;      p += ((size_t)dm.maxm * sizeof(int) + 15) / 16 * 16;
+  p = (unsigned char*)(((uintptr_t)p + 15) / 16 * 16);
+  cd* tile = (cd*)p;          p += (size_t)QT * RCH * sizeof(cd);
+  cd* ksred = (cd*)p;         p += (size_t)NT * RCH * sizeof(cd);
+  JacobiScratch js;
+  const int h = dm.dmax / 2 + 2;
+  js.e = (cd*)p;              p += (size_t)h * sizeof(cd);
+  js.cs = (double*)p;         p += (size_t)h * sizeof(double);
+  js.sn = (double*)p;         p += (size_t)h * sizeof(double);
+  double* s2 = (double*)p;    p += (size_t)dm.dmax * sizeof(double);
+  int* ord = (int*)p;         p += (size_t)dm.dmax * sizeof(int);
+  p = (unsigned char*)(((uintptr_t)p + 15) / 16 * 16);
+  double* red = (double*)p;   p += 16 * NW * sizeof(double);
+  js.gscale = (double*)p;     p += 8;
+  js.flag = (int*)p;          p += 8;
+
+  cd* ws = wsbase + (size_t)blockIdx.x * dm.ws_stride;
+  cd* Acm = ws;
+  cd* G = Acm + (size_t)dm.maxm * dm.n;
+  cd* V = G + (size_t)dm.dmax * dm.dmax;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = dm.n;
+
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const SpecTask tk = tasks[t];
+    const int m = tk.m, r = tk.r;
+    const double asc = *tk.A.scale, bsc = *tk.bscale;
+    const bool gram = (m <= n);
+    const int d = gram ? m : n;
+    for (int i = tid; i < m; i += NT) {
+      rows_s[i] = tk.A.rows ? tk.A.rows[i] : i;
+      Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
+    }
+    __syncthreads();
+    // row norms of A_eff and the row weights B_i / |a_i|   (:542-547; zero rows are left alone)
+    for (int i = warp; i < m; i += NW) {
+      const cd* row = tk.A.base + (size_t)rows_s[i] * n;
+      double a = 0.0;
+      for (int k = lane; k < n; k += 32) a += cabs2(row[k]);
+      a = warp_sum(a);
+      if (lane == 0) {
+        const double an = sqrt(a) * fabs(asc);
+        wrow[i] = (an != 0.0) ? Bs[i] / an : 1.0;
+      }
+    }
+    __syncthreads();
+    // As (column-major, weights folded in)
+    for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {
+      const int k = (int)(idx % n), i = (int)(idx / n);
+      const cd a = tk.A.base[(size_t)rows_s[i] * n + k];
+      const double w = asc * wrow[i];
+      Acm[i + (size_t)m * k] = cmk(a.x * w, a.y * w);
+    }
+    __syncthreads();
+    if (gram) {   // G = As As'  (m x m)
+      for (int idx = tid; idx < m * m; idx += NT) {
+        const int i = idx % m, j = idx / m;
+        if (i >= j) {
+          cd acc = cmk(0.0, 0.0);
+          for (int k = 0; k < n; ++k) cfmabc(acc, Acm[i + (size_t)m * k], Acm[j + (size_t)m * k]);
+          if (i == j) acc.y = 0.0;
+          G[i + (size_t)d * j] = acc;
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < m * m; idx += NT) {
+        const int i = idx % m, j = idx / m;
+        if (i < j) { cd u = G[j + (size_t)d * i]; G[i + (size_t)d * j] = cmk(u.x, -u.y); }
+      }
+    } else {      // G = As' As  (n x n)
+      for (size_t idx = tid; idx < (size_t)n * n; idx += NT) {
+        const int k = (int)(idx % n), l = (int)(idx / n);
+        if (k >= l) {
+          cd acc = cmk(0.0, 0.0);
+          for (int i = 0; i < m; ++i) cfmac(acc, Acm[i + (size_t)m * k], Acm[i + (size_t)m * l]);
+          // G[k,l] = sum_i conj(As[i,k]) As[i,l]
+          if (k == l) acc.y = 0.0;
+          G[k + (size_t)d * l] = acc;
+        }
+      }
+      __syncthreads();
+      for (size_t idx = tid; idx < (size_t)n * n; idx += NT) {
+        const int k = (int)(idx % n), l = (int)(idx / n);
+        if (k < l) { cd u = G[l + (size_t)d * k]; G[k + (size_t)d * l] = cmk(u.x, -u.y); }
+      }
+    }
+    __syncthreads();
+    const int sw = jacobi_heig(G, d, V, d, d, true, js, 60);
+    if (tid == 0 && tk.sweeps) *tk.sweeps = sw;
+    // clamp (:550) and rank by descending eigenvalue, stable (:551)
+    for (int i = tid; i < d; i += NT) s2[i] = fmax(0.0, G[i + (size_t)d * i].x);
+    __syncthreads();
+    for (int i = tid; i < d; i += NT) {
+      const double v = s2[i];
+      int rank = 0;
+      for (int j = 0; j < d; ++j) rank += (s2[j] > v) || (s2[j] == v && j < i);
+      ord[rank] = i;
+    }
+    __syncthreads();
+    if (gram) {   // Xs[:, c] = As' W[:, ord[c]]  (zero column when c >= m)
+      gemm_tpo(n, m, min(r, d),
+               [&](int i, int k) -> cd { cd a = tk.A.base[(size_t)rows_s[i] * n + k]; return cmk(a.x, -a.y); },
+               [&](int i, int c) -> cd { return cscale(V[i + (size_t)d * ord[c]], wrow[i]); },
+               [&](int k, int c, cd v) { tk.Xs[k + (size_t)n * c] = cscale(v, asc); }, tile, ksred);
+      for (size_t idx = (size_t)n * min(r, d) + tid; idx < (size_t)n * r; idx += NT) tk.Xs[idx] = cmk(0.0, 0.0);
+    } else {
+      for (size_t idx = tid; idx < (size_t)n * r; idx += NT) {
+        const int k = (int)(idx % n), c = (int)(idx / n);
+        const int j = ord[c];
+        tk.Xs[idx] = cscale(V[k + (size_t)d * j], sqrt(s2[j]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- column orthonormalisation  [Vx,~] = eig(X'*X); X = X*Vx  (inferLowRankV4.m:242-243) ------
+struct OrthoTask {
+  cd* X;               // n x r, in place
+  int r;
+  const int* active; int active_expect;
+};
+
+__host__ __device__ inline size_t ortho_smem_bytes(int rmax) {
+  return 2 * (size_t)rmax * rmax * sizeof(cd) + (size_t)(rmax / 2 + 2) * (sizeof(cd) + 2 * sizeof(double)) +
+         (size_t)rmax * (sizeof(double) + sizeof(int)) + (size_t)NT * RCH * sizeof(cd) + 16 * NW * sizeof(double) + 128;
+}
+
+__global__ void __launch_bounds__(NT, 2)
+ortho_kernel(const OrthoTask* __restrict__ tasks, int ntasks, int n, int rmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  cd* G = (cd*)p;  p += (size_t)rmax * rmax * sizeof(cd);
+  cd* V = (cd*)p;  p += (size_t)rmax * rmax * sizeof(cd);
+  cd* zt = (cd*)p; p += (size_t)NT * RCH * sizeof(cd);
+  JacobiScratch js;
+  const int h = rmax / 2 + 2;
+  js.e = (cd*)p;        p += (size_t)h * sizeof(cd);
+  js.cs = (double*)p;   p += (size_t)h * sizeof(double);
+  js.sn = (double*)p;   p += (size_t)h * sizeof(double);
+  double* ev = (double*)p; p += (size_t)rmax * sizeof(double);
+  js.gscale = (double*)p;  p += 8;
+  int* ord = (int*)p;   p += (size_t)rmax * sizeof(int);
+  js.flag = (int*)p;    p += 8;
+  const int tid = threadIdx.x;
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const OrthoTask tk = tasks[t];
+    if (tk.active != nullptr && *tk.active != tk.active_expect) continue;
+    const int r = tk.r;
+    const int pitch = r | 1;
+    const int KT = min(64, (NT * RCH) / pitch);
+    for (int idx = tid; idx < r * r; idx += NT) G[idx] = cmk(0.0, 0.0);
+    for (int k0 = 0; k0 < n; k0 += KT) {
+      const int kc = min(KT, n - k0);
+      __syncthreads();
+      for (int idx = tid; idx < kc * r; idx += NT) {
+        const int kl = idx % kc, c = idx / kc;
+        zt[kl * pitch + c] = tk.X[(size_t)(k0 + kl) + (size_t)n * c];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < r * r; idx += NT) {
+        const int c = idx % r, c2 = idx / r;
+        cd acc = cmk(0.0, 0.0);
+        for (int kl = 0; kl < kc; ++kl) cfmac(acc, zt[kl * pitch + c], zt[kl * pitch + c2]);
+        cd g = G[idx];
+        G[idx] = cmk(g.x + acc.x, g.y + acc.y);
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += NT) {
+      const int i = idx % r, j = idx / r;
+      if (i == j) G[idx].y = 0.0;
+      else if (i > j) { cd u = G[j + r * i]; G[idx] = cmk(u.x, -u.y); }
+    }
+    __syncthreads();
+    jacobi_heig(G, r, V, r, r, true, js, 60);
+    if (tid < r) ev[tid] = G[tid + r * tid].x;
+    __syncthreads();
+    if (tid < r) {   // ascending order like MATLAB's eig of a Hermitian matrix
+      const double v = ev[tid];
+      int rank = 0;
+      for (int j = 0; j < r; ++j) rank += (ev[j] < v) || (ev[j] == v && j < tid);
+      ord[rank] = tid;
+    }
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += KT) {
+      const int kc = min(KT, n - k0);
+      __syncthreads();
+      for (int idx = tid; idx < kc * r; idx += NT) {
+        const int kl = idx % kc, c = idx / kc;
+        zt[kl * pitch + c] = tk.X[(size_t)(k0 + kl) + (size_t)n * c];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < kc * r; idx += NT) {
+        const int kl = idx % kc, c2 = idx / kc;
+        const cd* vc = V + (size_t)r * ord[c2];
+        cd acc = cmk(0.0, 0.0);
+        for (int c = 0; c < r; ++c) cfma(acc, zt[kl * pitch + c], vc[c]);
+        tk.X[(size_t)(k0 + kl) + (size_t)n * c2] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- held-out quality + trial bookkeeping (inferLowRankV4.m:54-63, _multi.m:68-83) -------------
+struct QualTask {
+  AView A;             // test rows
+  const double* B; const int* brows; const double* bscale;
+  int mte;
+  const cd* x;         // n
+  const cd* y;         // m_train (for the best-trial copy)
+  int mtr;
+  cd* xmax; cd* ymax;  // best-trial buffers
+  InstCtl* ctl;
+  int trial;
+  int pass;            // 0: after the first impl run; 1: after the (masked) rank-one rerun
+  int multi;           // 1: keep the best of the trials; 0: always take the current trial
+};
+
+__global__ void __launch_bounds__(NT) quality_kernel(const QualTask* __restrict__ tasks, int ntasks, int n) {
+  __shared__ double red[16 * NW];
+  __shared__ int s_take;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const QualTask tk = tasks[t];
+    InstCtl* ctl = tk.ctl;
+    const bool compute = (tk.pass == 0) || (ctl->need_r1 == 1);
+    __syncthreads();
+    if (compute) {
+      const double asc = *tk.A.scale, bsc = *tk.bscale;
+      double v[2] = {0.0, 0.0};
+      for (int i = warp; i < tk.mte; i += NW) {
+        const int ri = tk.A.rows ? tk.A.rows[i] : i;
+        const cd* row = tk.A.base + (size_t)ri * n;
+        cd acc = cmk(0.0, 0.0);
+        for (int k = lane; k < n; k += 32) cfma(acc, row[k], tk.x[k]);
+        acc.x = warp_sum(acc.x);
+        acc.y = warp_sum(acc.y);
+        if (lane == 0) {
+          const double b = bsc * tk.B[tk.brows ? tk.brows[i] : i];
+          const double d = sqrt(cabs2(acc)) * fabs(asc) - b;
+          v[0] += d * d;
+          v[1] += b * b;
+        }
+      }
+      block_sum<2>(v, red);
+      if (tid == 0) {
+        const double q = 1.0 - sqrt(v[0]) / sqrt(v[1]);
+        ctl->quality = q;
+        if (tk.pass == 0) {
+          const int nr1 = (q < 0.6) ? 1 : 0;     // NaN -> no rerun, like MATLAB's comparison
+          ctl->need_r1 = nr1;
+          ctl->use_rank_one = nr1;
+          if (nr1) ctl->trial_r1_mask |= (1 << tk.trial);
+        }
+      }
+      __syncthreads();
+    }
+    if (tk.pass == 1) {
+      if (tid == 0) {
+        const double q = ctl->quality;
+        ctl->trial_quality[tk.trial] = q;
+        int take = tk.multi ? (ctl->max_quality < q) : 1;
+        if (take) { ctl->max_quality = q; ctl->best_trial = tk.trial; }
+        ctl->need_r1 = 0;
+        s_take = take;
+      }
+      __syncthreads();
+      if (s_take) {
+        for (int k = tid; k < n; k += NT) tk.xmax[k] = tk.x[k];
+        for (int i = tid; i < tk.mtr; i += NT) tk.ymax[i] = tk.y[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- refine roll-back and output scaling (inferLowRankV4.m:68-86) -------------------------------
+struct FinalTask {
+  const cd* x0; const cd* y0;   // best-trial solution (n, m_train)
+  const cd* xr; const cd* yr;   // refined solution (n, m)
+  int m, mtr;
+  cd* Xout; cd* Yout;           // n, m
+  double* quality_out;
+  InstCtl* ctl;
+};
+
+__global__ void __launch_bounds__(NT) final_kernel(const FinalTask* __restrict__ tasks, int ntasks, int n) {
+  __shared__ double red[16 * NW];
+  const int tid = threadIdx.x;
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const FinalTask tk = tasks[t];
+    InstCtl* ctl = tk.ctl;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = tid; k < n; k += NT) {
+      const cd a = tk.x0[k], b = tk.xr[k];
+      const cd d = cmulc(a, b);    // conj(x0) * x
+      v[0] += d.x; v[1] += d.y; v[2] += cabs2(a); v[3] += cabs2(b);
+    }
+    block_sum<4>(v, red);
+    const double q = ctl->quality;
+    const double sim = sqrt(v[0] * v[0] + v[1] * v[1]) / sqrt(v[2]) / sqrt(v[3]);
+    const bool rollback = (q > 0.6) && (sim < 0.6);
+    const double os = ctl->out_scale;
+    const cd* xs = rollback ? tk.x0 : tk.xr;
+    const cd* ys = rollback ? tk.y0 : tk.yr;
+    const int yr = rollback ? tk.mtr : tk.m;
+    for (int k = tid; k < n; k += NT) tk.Xout[k] = cscale(xs[k], os);
+    for (int i = tid; i < tk.m; i += NT) tk.Yout[i] = (i < yr) ? cscale(ys[i], os) : cmk(0.0, 0.0);
+    if (tid == 0) {
+      if (q > 0.6) ctl->similarity = sim;
+      ctl->rolled_back = rollback ? 1 : 0;
+      ctl->y_rows = yr;
+      *tk.quality_out = q;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void fill_nan_kernel(cd* p, size_t nelem) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = cmk(NAN, NAN);
+}
+
+}  // namespace twoace

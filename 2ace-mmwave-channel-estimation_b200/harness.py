@@ -1,0 +1,145 @@
+"""Synthetic instance generator and metrics for the ADMM CSI-recovery path (host side, NumPy).
+
+Restates, for input synthesis only (SURVEY.md §8d "Config 1"):
+
+* Eq. 23 sparse multipath channel — ``Numerical_Simulation/src/generate_channel/Generate_Channel.m:64-142``
+  (L>1 => no Rician tail, ``:98-106``; ``vecH = vec(H_Matrix)`` with ``H_Matrix`` Nr x Nt, ``:139``)
+* measurement model ``|FW*vecH + noise|`` with signal power 1 —
+  ``Numerical_Simulation/src/generate_measurement/Generate_Measurement.m:84-101``
+* 2-bit random beams — ``Numerical_Simulation/src/Generate_random_beam.m:31-34``
+* NMSE — ``Numerical_Simulation/src/evaluate_plot_results/Evaluation_H.m:81-89``
+
+MATLAB's randn/randperm/randsample streams cannot be reproduced outside MATLAB, so the
+generator uses a documented NumPy stream: one ``SeedSequence`` child per trial, draw order
+``[AoD, AoA, gains, row subset, noise, train_idx (x3)]``.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+# first entry of the 40 hard-coded seeds of channel_recovery_ADMM_v2_simulation_A2only.m:103
+BASE_SEED = 58659179
+
+WAVELENGTH = 3e8 / 60.48e9   # A2only.m:38
+ANT_SPACING = 3.055e-3       # A2only.m:39
+SEARCHING_AREA = 95.0        # A2only.m:52
+
+_ROOTS = np.array([1, 1j, -1, -1j], dtype=np.complex128)
+
+
+def unpack_codes(packed: np.ndarray, shape) -> np.ndarray:
+    """2-bit phase codes (4 per byte, little-endian in the byte) -> uint8 array of ``shape``."""
+    p = np.asarray(packed, dtype=np.uint8)
+    k = np.stack([(p >> s) & 3 for s in (0, 2, 4, 6)], axis=1).reshape(-1)
+    return k.reshape(tuple(int(x) for x in shape))
+
+
+def load_codebook_codes(name: str = "random_probe_cb_16x16") -> np.ndarray:
+    """Phase codes k (uint8, exp(1j*k*pi/2)) of a shipped codebook (fixture built from
+    ``codebook/codebook_mat/<name>.mat`` by ``tests/golden/make_codebook_fixture.py``)."""
+    z = np.load(os.path.join(_DATA, name + ".u2.npz"))
+    return unpack_codes(z["codes"], z["shape"])
+
+
+def load_codebook(name: str = "random_probe_cb_16x16") -> np.ndarray:
+    """Complex128 codebook ``cb`` with exact unit-modulus 4-phase entries."""
+    return _ROOTS[load_codebook_codes(name)]
+
+
+def random_beam_codes(rng: np.random.Generator, rows: int, n: int, phase_bit: int = 2) -> np.ndarray:
+    """Random Np-phase beam codes (Generate_random_beam.m:31-34, Np = Phase_Bit^2)."""
+    return rng.integers(0, phase_bit ** 2, size=(rows, n), dtype=np.uint8)
+
+
+def generate_channel(rng: np.random.Generator, Nt: int, Nr: int, L: int = 3,
+                     searching_area: float = SEARCHING_AREA, lam: float = WAVELENGTH,
+                     d: float = ANT_SPACING):
+    """Eq. 23 channel (Generate_Channel.m:76-139). Returns (H [Nr x Nt], vecH [Nt*Nr], AoD, AoA)."""
+    half = searching_area / 2
+    aod = rng.uniform(-half, half, L)
+    aoa = rng.uniform(-half, half, L)
+    g = (rng.standard_normal(L) + 1j * rng.standard_normal(L)) / math.sqrt(2)
+    g = g / np.linalg.norm(g)
+    kt = np.arange(Nt)[:, None]
+    kr = np.arange(Nr)[:, None]
+    ATx = np.exp(-1j * 2 * np.pi / lam * d * np.sin(np.deg2rad(aod))[None, :] * kt) / math.sqrt(Nt)
+    ARx = np.exp(-1j * 2 * np.pi / lam * d * np.sin(np.deg2rad(aoa))[None, :] * kr) / math.sqrt(Nr)
+    H = math.sqrt(Nt * Nr) * (ARx * g[None, :]) @ ATx.conj().T
+    return H, H.reshape(-1, order="F"), aod, aoa
+
+
+@dataclass
+class Instance:
+    rows: np.ndarray        # int32 [m] codebook row ids (bit-exact bookkeeping)
+    A: np.ndarray           # complex128 [m, n] sensing matrix handed to the solver
+    B: np.ndarray           # float64 [m] RSS amplitudes |y|
+    train_idx: np.ndarray   # int32 [3, floor(m*cc_frac)] the three randsample draws (0-based)
+    vecH: np.ndarray        # complex128 [n] ground truth
+    snr_db: float
+
+
+def make_instance(seed: np.random.SeedSequence, cb: np.ndarray, M: int, snr_db: float,
+                  Nt: int = 16, Nr: int = 16, L: int = 3, cc_frac: float = 0.95,
+                  row_range=None) -> Instance:
+    """One (trial, M, SNR) instance of SURVEY.md §8(d) config 1/2/4.
+
+    ``cb`` [rows x n] unit-modulus codebook; sensing rows are ``cb[rows]/sqrt(n)`` (unit-norm rows so
+    that signal power is 1, Generate_Measurement.m:84).  ``row_range`` = (lo, hi) restricts the draw to
+    a resolution stage of the multires codebook (…simulation_multiresolution.m:137-143).
+    """
+    rng = np.random.default_rng(seed)
+    n = Nt * Nr
+    _, vecH, _, _ = generate_channel(rng, Nt, Nr, L)
+    lo, hi = (0, cb.shape[0]) if row_range is None else row_range
+    rows = (lo + rng.permutation(hi - lo)[:M]).astype(np.int32)
+    A = cb[rows, :] / math.sqrt(n)
+    noise_power = 10.0 ** (-snr_db / 10.0)
+    w = math.sqrt(noise_power / 2) * (rng.standard_normal(M) + 1j * rng.standard_normal(M))
+    B = np.abs(A @ vecH + w)
+    k = int(math.floor(M * cc_frac))
+    train = np.stack([rng.permutation(M)[:k] for _ in range(3)]).astype(np.int32)
+    return Instance(rows, A, B, train, vecH, snr_db)
+
+
+def make_batch(n_trials: int, cb: np.ndarray, M, snr_db, base_seed: int = BASE_SEED,
+               first_trial: int = 0, **kw):
+    """``n_trials`` instances; trial t uses child t of ``SeedSequence(base_seed)`` regardless of how
+    trials are sharded over ranks.  ``M``/``snr_db`` scalar or per-trial sequences."""
+    kids = np.random.SeedSequence(base_seed).spawn(first_trial + n_trials)[first_trial:]
+    Ms = np.broadcast_to(np.asarray(M), (n_trials,))
+    snrs = np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (n_trials,))
+    return [make_instance(kids[t], cb, int(Ms[t]), float(snrs[t]), **kw) for t in range(n_trials)]
+
+
+# ----------------------------------------------------------------------------------- metrics
+def nmse(x: np.ndarray, x_gt: np.ndarray) -> float:
+    """Scale/phase-invariant MSE_H of Evaluation_H.m:87-89."""
+    x = np.asarray(x).reshape(-1)
+    x_gt = np.asarray(x_gt).reshape(-1)
+    xx = np.vdot(x, x)
+    if not np.isfinite(xx) or xx == 0:
+        return float("nan")
+    return float(np.linalg.norm(x_gt - (np.vdot(x, x_gt) / xx) * x) ** 2 / np.linalg.norm(x_gt) ** 2)
+
+
+def nmse_db(values) -> float:
+    """10*log10(mean MSE_H) (Plot_result.m:154)."""
+    return float(10 * np.log10(np.nanmean(np.asarray(values, dtype=np.float64))))
+
+
+def aligned_rel_err(x: np.ndarray, x_ref: np.ndarray) -> float:
+    """||x*e^{j phi} - x_ref|| / ||x_ref|| after the global-phase alignment of Evaluation_H.m:81-82."""
+    x = np.asarray(x).reshape(-1)
+    x_ref = np.asarray(x_ref).reshape(-1)
+    if not (np.all(np.isfinite(x)) and np.all(np.isfinite(x_ref))):
+        both_nan = np.array_equal(np.isnan(x), np.isnan(x_ref))
+        return 0.0 if both_nan and np.isnan(x).all() else float("inf")
+    ph = np.exp(1j * np.angle(np.vdot(x, x_ref)))
+    den = np.linalg.norm(x_ref)
+    return float(np.linalg.norm(x * ph - x_ref) / (den if den > 0 else 1.0))

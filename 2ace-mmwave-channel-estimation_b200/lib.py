@@ -1,0 +1,184 @@
+"""ctypes binding of libtwoace (include/twoace.h).  There is no CPU fallback: if the CUDA shared
+library is missing or no GPU is present the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtwoace.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+V4, V4_MULTI, NUCLEAR = 0, 1, 2
+INFO_WORDS = 16
+STAGE_WORDS = 12
+
+# every symbol include/twoace.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "twoace_default_params", "twoace_version", "twoace_create", "twoace_destroy", "twoace_last_error",
+    "twoace_stream", "twoace_launch_count", "twoace_synchronize", "twoace_solve_batch",
+    "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
+    "twoace_spectral_init_batch",
+]
+
+
+class Params(C.Structure):
+    """twoace_params (inferLowRankV4.m:2-9 defaults)."""
+    _fields_ = [("lam", C.c_double), ("r", C.c_int32), ("mu0", C.c_double), ("rho", C.c_double),
+                ("cc_frac", C.c_double), ("tol_rel", C.c_double), ("tol_abs", C.c_double),
+                ("maxiter", C.c_int32)]
+
+    @classmethod
+    def default(cls, **kw) -> "Params":
+        p = cls(0.0, 20, 1e-3, 1.03, 0.95, 1e-4, 1e-8, 500)
+        for k, v in kw.items():
+            if k == "lambda_":
+                k = "lam"
+            if not hasattr(p, k):
+                raise TypeError(f"unknown solver parameter {k!r}")
+            setattr(p, k, v)
+        return p
+
+    def fixed_iters(self) -> "Params":
+        q = Params(self.lam, self.r, self.mu0, self.rho, self.cc_frac, 0.0, 0.0, self.maxiter)
+        return q
+
+
+class TwoaceError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libtwoace.so (built in-tree by __graft_entry__.build()); fail loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TwoaceError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, dp = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.twoace_default_params.argtypes = [C.POINTER(Params)]
+    lib.twoace_default_params.restype = None
+    lib.twoace_version.restype = C.c_int
+    lib.twoace_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.twoace_create.restype = C.c_int
+    lib.twoace_destroy.argtypes = [vp]
+    lib.twoace_destroy.restype = None
+    lib.twoace_last_error.argtypes = [vp]
+    lib.twoace_last_error.restype = C.c_char_p
+    lib.twoace_stream.argtypes = [vp]
+    lib.twoace_stream.restype = vp
+    lib.twoace_launch_count.argtypes = [vp]
+    lib.twoace_launch_count.restype = C.c_int64
+    lib.twoace_synchronize.argtypes = [vp]
+    lib.twoace_synchronize.restype = C.c_int
+    lib.twoace_solve_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, dp, i32p,
+                                       C.POINTER(Params), dp, dp, dp, dp, dp]
+    lib.twoace_solve_batch.restype = C.c_int
+    lib.twoace_set_codebook.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+    lib.twoace_set_codebook.restype = C.c_int
+    lib.twoace_solve_batch_codebook.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p,
+                                                C.c_double, dp, i32p, C.POINTER(Params), dp, dp, dp, dp, dp]
+    lib.twoace_solve_batch_codebook.restype = C.c_int
+    lib.twoace_infer_admm_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, dp, C.c_int, dp,
+                                            C.c_int, C.c_int, C.c_int, C.POINTER(Params), dp, dp, dp, dp]
+    lib.twoace_infer_admm_batch.restype = C.c_int
+    lib.twoace_spectral_init_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, dp, dp, C.c_int, dp]
+    lib.twoace_spectral_init_batch.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Host pointer of a NumPy array, raw int for device pointers, None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """twoace_ctx wrapper (one per GPU / process)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.twoace_create(int(device), C.byref(h))
+        if rc != 0 or not h.value:
+            raise TwoaceError(f"twoace_create(device={device}) failed with code {rc}: no usable CUDA device "
+                              "(the product path has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.twoace_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.twoace_last_error(self.h)
+            raise TwoaceError(f"libtwoace error {rc}: {msg.decode() if msg else '?'}")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.twoace_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.twoace_launch_count(self.h))
+
+    def synchronize(self):
+        self.check(self.lib.twoace_synchronize(self.h))
+
+    # ---- raw entry points (pointers may be NumPy arrays (host) or ints (device addresses)) ----
+    def solve_batch_raw(self, variant, mem, nb, tx, rx, m, A, B, train_idx, params, X, Y, quality, info=None,
+                        stage_words=None):
+        self.check(self.lib.twoace_solve_batch(self.h, variant, mem, nb, tx, rx, _ptr(m), _ptr(A), _ptr(B),
+                                               _ptr(train_idx), C.byref(params), _ptr(X), _ptr(Y), _ptr(quality),
+                                               _ptr(info), _ptr(stage_words)))
+
+    def set_codebook(self, cb: np.ndarray):
+        """cb: rows x n complex128 (any layout); uploaded column-major like the .mat variable."""
+        cbf = np.asfortranarray(cb, dtype=np.complex128)
+        flat = np.ascontiguousarray(cbf.reshape(-1, order="F"))
+        self.check(self.lib.twoace_set_codebook(self.h, MEM_HOST, cb.shape[0], cb.shape[1], _ptr(flat)))
+
+    def solve_batch_codebook_raw(self, variant, mem, nb, tx, rx, m, cb_rows, row_scale, B, train_idx, params, X, Y,
+                                 quality, info=None, stage_words=None):
+        self.check(self.lib.twoace_solve_batch_codebook(self.h, variant, mem, nb, tx, rx, _ptr(m), _ptr(cb_rows),
+                                                        float(row_scale), _ptr(B), _ptr(train_idx),
+                                                        C.byref(params), _ptr(X), _ptr(Y), _ptr(quality),
+                                                        _ptr(info), _ptr(stage_words)))
+
+    def infer_admm_batch_raw(self, mem, nb, tx, rx, m, A, B, r, X0, sbr, rank_one, nuclear, params, X, Y,
+                             state=None, words=None):
+        self.check(self.lib.twoace_infer_admm_batch(self.h, mem, nb, tx, rx, _ptr(m), _ptr(A), _ptr(B), r, _ptr(X0),
+                                                    int(sbr), int(rank_one), int(nuclear), C.byref(params),
+                                                    _ptr(X), _ptr(Y), _ptr(state), _ptr(words)))
+
+    def spectral_init_batch_raw(self, mem, nb, n, m, A, B, r, Xs):
+        self.check(self.lib.twoace_spectral_init_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(B), r, _ptr(Xs)))
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

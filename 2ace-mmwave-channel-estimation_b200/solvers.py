@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's solver interface for the ADMM hot path.
+
+Same names, argument meaning and outputs as the MATLAB functions they replace:
+
+* ``inferLowRankV4``        — main/src/my_recovery_algorithms/ADMM_v2/inferLowRankV4.m:1-9
+* ``inferLowRankV4_multi``  — …/inferLowRankV4_multi.m:5-13
+* ``inferLowRank_Nuclear``  — …/inferLowRank_Nuclear.m:5-13
+* ``ADMM_v2`` / ``ADMM_v2_nuclear`` — main/src/my_recovery_algorithms/ADMM_v2.m:1,22-45, ADMM_v2_nuclear.m:32,
+  Numerical_Simulation/src/my_recovery_algorithms/ADMM_v2/ADMM_v2.m:22-41 (``tree='ns'``)
+
+plus the batched forms the single-instance calls are built on.  All arithmetic runs in the CUDA
+library (``lib.py`` -> ``libtwoace.so``); this file only marshals arrays.  The reference draws its
+train/test split from MATLAB's global RNG (``randsample``, inferLowRankV4.m:37), which cannot be
+reproduced outside MATLAB: pass ``train_idx`` (0-based, drawn order) to pin the split, otherwise it
+is drawn from ``rng`` (NumPy ``Generator``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import NUCLEAR, V4, V4_MULTI, Params
+
+__all__ = ["inferLowRankV4", "inferLowRankV4_multi", "inferLowRank_Nuclear", "ADMM_v2", "ADMM_v2_nuclear",
+           "solve_batch", "solve_batch_codebook", "infer_admm_batch", "spectral_init_batch", "BatchResult",
+           "draw_train_idx"]
+
+
+def _params(lambda_, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter) -> Params:
+    return Params(float(lambda_), int(r), float(mu0), float(rho), float(cc_frac), float(tol_rel),
+                  float(tol_abs), int(maxiter))
+
+
+def draw_train_idx(m: int, cc_frac: float, ntrial: int, rng: np.random.Generator) -> np.ndarray:
+    """The randsample(m, floor(m*cc_frac)) draws of inferLowRankV4.m:37 from a NumPy stream."""
+    k = int(math.floor(m * cc_frac))
+    return np.stack([rng.permutation(m)[:k] for _ in range(ntrial)]).astype(np.int32)
+
+
+@dataclass
+class BatchResult:
+    X: np.ndarray            # [nb, n] complex128
+    Y: list                  # nb arrays [y_rows_b] complex128
+    quality: np.ndarray      # [nb]
+    info: np.ndarray         # [nb, 16] (twoace.h TWOACE_INFO_WORDS)
+    stage_words: np.ndarray  # [nb, 4T+1, 12]
+
+
+def _concat_inputs(A_list, B_list, train_idx_list, ntrial, cc_frac, n):
+    nb = len(A_list)
+    m = np.array([np.shape(a)[0] for a in A_list], dtype=np.int32)
+    for a in A_list:
+        if np.shape(a)[1] != n:
+            raise ValueError(f"A must have tx*rx = {n} columns, got {np.shape(a)[1]}")
+    A = np.concatenate([np.asarray(a, dtype=np.complex128).reshape(-1, order="F") for a in A_list]) if nb else \
+        np.zeros(0, np.complex128)
+    B = np.concatenate([np.asarray(b, dtype=np.float64).reshape(-1) for b in B_list]) if nb else np.zeros(0)
+    tr = []
+    for b in range(nb):
+        t = np.asarray(train_idx_list[b], dtype=np.int32).reshape(ntrial, -1)
+        k = int(math.floor(int(m[b]) * cc_frac))
+        if t.shape[1] != k:
+            raise ValueError(f"instance {b}: train_idx needs floor(m*cc_frac) = {k} entries per draw, got {t.shape[1]}")
+        tr.append(t.reshape(-1))
+    T = np.concatenate(tr) if nb else np.zeros(0, np.int32)
+    return m, np.ascontiguousarray(A), np.ascontiguousarray(B), np.ascontiguousarray(T.astype(np.int32))
+
+
+def _unpack(nb, n, m, X, Y, q, info, sw, ntrial):
+    offs = np.concatenate([[0], np.cumsum(m)])
+    info = info.reshape(nb, _lib.INFO_WORDS)
+    Ys = [Y[offs[b]:offs[b] + int(info[b, 5])].copy() for b in range(nb)]
+    return BatchResult(X.reshape(nb, n), Ys, q, info, sw.reshape(nb, 4 * ntrial + 1, _lib.STAGE_WORDS))
+
+
+def solve_batch(variant: int, A_list, B_list, tx: int, rx: int, train_idx_list, params: Params | None = None,
+                ctx: _lib.Context | None = None) -> BatchResult:
+    """Batched inferLowRankV4 / _multi / _Nuclear on dense per-instance A (ragged m)."""
+    ctx = ctx or _lib.default_context()
+    p = params or Params.default()
+    nb, n = len(A_list), tx * rx
+    ntrial = 3 if variant == V4_MULTI else 1
+    m, A, B, T = _concat_inputs(A_list, B_list, train_idx_list, ntrial, p.cc_frac, n)
+    X = np.empty(nb * n, np.complex128)
+    Y = np.empty(int(m.sum()), np.complex128)
+    q = np.empty(nb, np.float64)
+    info = np.empty(nb * _lib.INFO_WORDS, np.float64)
+    sw = np.empty(nb * (4 * ntrial + 1) * _lib.STAGE_WORDS, np.float64)
+    ctx.solve_batch_raw(variant, _lib.MEM_HOST, nb, tx, rx, m, A, B, T, p, X, Y, q, info, sw)
+    return _unpack(nb, n, m, X, Y, q, info, sw, ntrial)
+
+
+def solve_batch_codebook(variant: int, rows_list, row_scale: float, B_list, tx: int, rx: int, train_idx_list,
+                         params: Params | None = None, ctx: _lib.Context | None = None) -> BatchResult:
+    """Same with A_b = row_scale * cb[rows_b] for the codebook registered by ``ctx.set_codebook``
+    (row selection of channel_recovery_ADMM_v2_simulation_A2only.m:137-138)."""
+    ctx = ctx or _lib.default_context()
+    p = params or Params.default()
+    nb, n = len(rows_list), tx * rx
+    ntrial = 3 if variant == V4_MULTI else 1
+    m = np.array([len(r) for r in rows_list], dtype=np.int32)
+    rows = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in rows_list]))
+    B = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float64).reshape(-1) for b in B_list]))
+    tr = []
+    for b in range(nb):
+        t = np.asarray(train_idx_list[b], dtype=np.int32).reshape(ntrial, -1)
+        k = int(math.floor(int(m[b]) * p.cc_frac))
+        if t.shape[1] != k:
+            raise ValueError(f"instance {b}: train_idx needs {k} entries per draw, got {t.shape[1]}")
+        tr.append(t.reshape(-1))
+    T = np.ascontiguousarray(np.concatenate(tr).astype(np.int32))
+    X = np.empty(nb * n, np.complex128)
+    Y = np.empty(int(m.sum()), np.complex128)
+    q = np.empty(nb, np.float64)
+    info = np.empty(nb * _lib.INFO_WORDS, np.float64)
+    sw = np.empty(nb * (4 * ntrial + 1) * _lib.STAGE_WORDS, np.float64)
+    ctx.solve_batch_codebook_raw(variant, _lib.MEM_HOST, nb, tx, rx, m, rows, row_scale, B, T, p, X, Y, q, info, sw)
+    return _unpack(nb, n, m, X, Y, q, info, sw, ntrial)
+
+
+def infer_admm_batch(A_list, B_list, X0_list, scale_by_row: bool, use_rank_one: bool, tx: int, rx: int,
+                     params: Params | None = None, nuclear: bool = False, ctx: _lib.Context | None = None):
+    """One InferADMM call per instance (inferLowRankV4.m:260-365).  Returns (X, Y, state, words) lists;
+    state[b] = dict(X, Z, N, Y, M) of the final iterate, words[b] = twoace.h stage words."""
+    ctx = ctx or _lib.default_context()
+    p = params or Params.default()
+    nb, n = len(A_list), tx * rx
+    r = int(np.shape(X0_list[0])[1]) if np.ndim(X0_list[0]) == 2 else 1
+    rout = r if scale_by_row else 1
+    m = np.array([np.shape(a)[0] for a in A_list], dtype=np.int32)
+    A = np.ascontiguousarray(np.concatenate([np.asarray(a, np.complex128).reshape(-1, order="F") for a in A_list]))
+    B = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1) for b in B_list]))
+    X0 = np.ascontiguousarray(np.concatenate(
+        [np.asarray(x, np.complex128).reshape(n, r).reshape(-1, order="F") for x in X0_list]))
+    X = np.empty(nb * n * rout, np.complex128)
+    Y = np.empty(int(m.sum()) * rout, np.complex128)
+    st_sizes = [3 * n * r + 2 * int(mm) * r for mm in m]
+    state = np.empty(int(sum(st_sizes)), np.complex128)
+    words = np.empty(nb * _lib.STAGE_WORDS, np.float64)
+    ctx.infer_admm_batch_raw(_lib.MEM_HOST, nb, tx, rx, m, A, B, r, X0, scale_by_row, use_rank_one, nuclear, p,
+                             X, Y, state, words)
+    Xs, Ys, Ss = [], [], []
+    yo = so = 0
+    for b in range(nb):
+        mb = int(m[b])
+        Xs.append(X[b * n * rout:(b + 1) * n * rout].reshape(n, rout, order="F").copy())
+        Ys.append(Y[yo:yo + mb * rout].reshape(mb, rout, order="F").copy())
+        yo += mb * rout
+        s = state[so:so + st_sizes[b]]
+        so += st_sizes[b]
+        nr, mr = n * r, mb * r
+        Ss.append(dict(X=s[:nr].reshape(n, r, order="F"), Z=s[nr:2 * nr].reshape(n, r, order="F"),
+                       N=s[2 * nr:3 * nr].reshape(n, r, order="F"),
+                       Y=s[3 * nr:3 * nr + mr].reshape(mb, r, order="F"),
+                       M=s[3 * nr + mr:].reshape(mb, r, order="F")))
+    return Xs, Ys, Ss, words.reshape(nb, _lib.STAGE_WORDS)
+
+
+def spectral_init_batch(A_list, B_list, r: int, ctx: _lib.Context | None = None):
+    """SpectralInitialize (inferLowRankV4.m:540-553) per instance -> list of n x r arrays."""
+    ctx = ctx or _lib.default_context()
+    nb = len(A_list)
+    n = int(np.shape(A_list[0])[1])
+    m = np.array([np.shape(a)[0] for a in A_list], dtype=np.int32)
+    A = np.ascontiguousarray(np.concatenate([np.asarray(a, np.complex128).reshape(-1, order="F") for a in A_list]))
+    B = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1) for b in B_list]))
+    Xs = np.empty(nb * n * r, np.complex128)
+    ctx.spectral_init_batch_raw(_lib.MEM_HOST, nb, n, m, A, B, r, Xs)
+    return [Xs[b * n * r:(b + 1) * n * r].reshape(n, r, order="F").copy() for b in range(nb)]
+
+
+# ----------------------------------------------------------------------------- MATLAB-signature calls
+def _single(variant, A, B, tx, rx, p: Params, train_idx, rng, ctx):
+    A = np.asarray(A, dtype=np.complex128)
+    m = A.shape[0]
+    ntrial = 3 if variant == V4_MULTI else 1
+    if train_idx is None:
+        train_idx = draw_train_idx(m, p.cc_frac, ntrial, rng or np.random.default_rng())
+    res = solve_batch(variant, [A], [B], int(tx), int(rx), [train_idx], p, ctx)
+    return res.X[0], res.Y[0], float(res.quality[0])
+
+
+def inferLowRankV4(A, B, tx, rx, lambda_=0.0, r=20, mu0=1e-3, rho=1.03, cc_frac=0.95, tol_rel=1e-4,
+                   tol_abs=1e-8, maxiter=500, *, train_idx=None, rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRankV4(A, B, tx, rx, lambda, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter)."""
+    return _single(V4, A, B, tx, rx, _params(lambda_, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
+def inferLowRankV4_multi(A, B, tx, rx, lambda_=0.0, r=20, mu0=1e-3, rho=1.03, cc_frac=0.95, tol_rel=1e-4,
+                         tol_abs=1e-8, maxiter=500, *, train_idx=None, rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRankV4_multi(...): three random restarts, best held-out quality kept."""
+    return _single(V4_MULTI, A, B, tx, rx, _params(lambda_, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
+def inferLowRank_Nuclear(A, B, tx, rx, lambda_=0.0, r=20, mu0=1e-3, rho=1.03, cc_frac=0.95, tol_rel=1e-4,
+                         tol_abs=1e-8, maxiter=500, *, train_idx=None, rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRank_Nuclear(...): singular-value soft-threshold ArgMinZ."""
+    return _single(NUCLEAR, A, B, tx, rx, _params(lambda_, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
+def ADMM_v2(measurements, FW, TX, RX, version, *, tree="main", train_idx=None, rng=None, ctx=None):
+    """[X, Y, converged] = ADMM_v2(measurements, FW, TX, RX, version).  As in the reference the third
+    output is really ``quality`` (ADMM_v2.m:31-32 vs inferLowRankV4.m:1).  Versions outside the
+    V4 family (SURVEY.md §2.2 rows 0-3 of ``main``) are not part of this build."""
+    B = np.asarray(measurements, dtype=np.float64).reshape(-1)
+    if tree == "main" and version == 4:
+        return inferLowRankV4_multi(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
+    if tree == "ns" and version == 3:
+        return inferLowRankV4(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
+    raise NotImplementedError(f"ADMM_v2 version {version} (tree {tree!r}) is outside the accelerated hot path")
+
+
+def ADMM_v2_nuclear(measurements, FW, TX, RX, version, *, train_idx=None, rng=None, ctx=None):
+    """ADMM_v2_nuclear.m: version 4 -> inferLowRank_Nuclear."""
+    B = np.asarray(measurements, dtype=np.float64).reshape(-1)
+    if version == 4:
+        return inferLowRank_Nuclear(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
+    raise NotImplementedError(f"ADMM_v2_nuclear version {version} is outside the accelerated hot path")

@@ -1,0 +1,138 @@
+/* twoace.h — C ABI of libtwoace: B200-native batched solver for 2ACE's ADMM CSI-recovery hot path.
+ *
+ * The reference has no FFI for this path; its boundary is the MATLAB function signature
+ *   [X,Y,quality] = inferLowRankV4(A,B,tx,rx,lambda,r,mu0,rho,cc_frac,tol_rel,tol_abs,maxiter)
+ * (main/src/my_recovery_algorithms/ADMM_v2/inferLowRankV4.m:1-9; same for inferLowRankV4_multi.m:5
+ * and inferLowRank_Nuclear.m:5), reached through ADMM_v2.m:22-45 / ADMM_v2_nuclear.m:32 and, from
+ * Python, through the MATLAB engine (main/main.py:231,308,427).  A MEX file of the same base name
+ * shadows the .m file; the MEX shim (mex/twoace_mex.cpp) and the ctypes binding
+ * (2ace-mmwave-channel-estimation_b200/lib.py) both sit on the entry points below.
+ *
+ * Conventions
+ *   - complex arrays are interleaved (re,im) doubles, matrices column-major (MATLAB layout);
+ *   - batches are ragged in m: per-instance arrays are concatenated in instance order;
+ *   - the MATLAB global RNG is externalised: the randsample() draws of inferLowRankV4.m:37
+ *     (inferLowRankV4_multi.m:48: three draws) are the `train_idx` input, 0-based, drawn order,
+ *     floor(m*cc_frac) entries per draw;
+ *   - `mem` says where ALL data pointers of a call live: TWOACE_MEM_HOST or TWOACE_MEM_DEVICE
+ *     (index arrays `m`, `train_idx`, `cb_rows` are always host pointers);
+ *   - every function returns 0 on success or a negative TWOACE_E_* code; twoace_last_error()
+ *     returns the message.  Numerical failures are not errors: NaN propagates as in the reference.
+ */
+#ifndef TWOACE_H
+#define TWOACE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct twoace_ctx twoace_ctx;
+
+enum {
+  TWOACE_OK = 0,
+  TWOACE_E_INVALID = -1,      /* bad argument */
+  TWOACE_E_UNSUPPORTED = -2,  /* valid in the reference but outside this build (e.g. lambda != 0) */
+  TWOACE_E_CUDA = -3,         /* CUDA runtime failure */
+  TWOACE_E_NOMEM = -4
+};
+
+enum { TWOACE_MEM_HOST = 0, TWOACE_MEM_DEVICE = 1 };
+
+/* Solver variant = which reference file is replaced. */
+enum {
+  TWOACE_V4 = 0,        /* inferLowRankV4.m        (NS ADMM_v2.m version 3)        */
+  TWOACE_V4_MULTI = 1,  /* inferLowRankV4_multi.m  (main ADMM_v2.m version 4)       */
+  TWOACE_NUCLEAR = 2    /* inferLowRank_Nuclear.m  (main ADMM_v2_nuclear.m version 4) */
+};
+
+/* Optional positional arguments of inferLowRankV4.m:2-9 (defaults in twoace_default_params). */
+typedef struct {
+  double lambda;   /* 0 (only value supported: the lambda != 0 eigen-path is dead in the reference) */
+  int32_t r;       /* 20 */
+  double mu0;      /* 1e-3 */
+  double rho;      /* 1.03 */
+  double cc_frac;  /* 0.95 */
+  double tol_rel;  /* 1e-4 */
+  double tol_abs;  /* 1e-8 */
+  int32_t maxiter; /* 500 */
+} twoace_params;
+
+#define TWOACE_INFO_WORDS 16
+/* info[b*16 + k]: 0 quality, 1 similarity (NaN if not computed), 2 use_rank_one (last trial),
+ * 3 rolled_back, 4 best_trial, 5 rows of returned Y, 6 bitmask of trials that re-ran rank-one,
+ * 7..9 per-trial quality, 10 max_quality, 11 refine iterations, 12 refine opt_iter,
+ * 13 refine final mu, 14 refine mu bumps, 15 total ADMM iterations over all stages. */
+
+#define TWOACE_STAGE_WORDS 12
+/* stage bookkeeping words (per InferADMM call): 0 mu, 1 opt_obj, 2 iters, 3 opt_iter (1-based),
+ * 4 opt_col (0-based, -1 for scale_by_row), 5 mu bumps, 6 converged, 7 last res_comb,
+ * 8 Jacobi sweeps, 9..11 reserved. */
+
+void twoace_default_params(twoace_params* p);
+
+/* Library / build identification (e.g. 100 = round 1). */
+int twoace_version(void);
+
+int twoace_create(int device, twoace_ctx** ctx);
+void twoace_destroy(twoace_ctx* ctx);
+const char* twoace_last_error(const twoace_ctx* ctx);
+/* CUDA stream the context launches on (cudaStream_t as void*), for event timing by callers. */
+void* twoace_stream(twoace_ctx* ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t twoace_launch_count(const twoace_ctx* ctx);
+/* Block until all work queued by the context has finished. */
+int twoace_synchronize(twoace_ctx* ctx);
+
+/* Full solve of nb independent instances — replaces inferLowRankV4 / _multi / _Nuclear
+ * (see the variant enum).  A is dense per instance.
+ *   m[nb]            rows per instance (host)
+ *   A                concat of m_b x n column-major complex matrices (n = tx*rx)
+ *   B                concat of m_b real RSS amplitudes
+ *   train_idx        host; per instance T draws of floor(m_b*cc_frac) ints (T = 3 for V4_MULTI else 1)
+ *   X                out, nb x n complex
+ *   Y                out, concat of m_b complex (rows beyond info[5] are zero after a roll-back)
+ *   quality          out, nb
+ *   info             out or NULL, nb x TWOACE_INFO_WORDS doubles (host or device per `mem`)
+ *   stage_words      out or NULL, nb x (4T+1) x TWOACE_STAGE_WORDS doubles; stage order per trial:
+ *                    over-param, refinement, rank-one over-param, rank-one refinement; then refine
+ */
+int twoace_solve_batch(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx,
+                       const int32_t* m, const double* A, const double* B, const int32_t* train_idx,
+                       const twoace_params* params, double* X, double* Y, double* quality,
+                       double* info, double* stage_words);
+
+/* Register a codebook shared by all instances: rows x n complex, column-major (the `cb` variable of
+ * codebook/codebook_mat/*.mat), host or device per `mem`.  Kept on the device until replaced. */
+int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, const double* cb);
+
+/* Same as twoace_solve_batch with A_b = row_scale * cb[cb_rows_b, :] (the row selection of
+ * channel_recovery_ADMM_v2_simulation_A2only.m:137-138).  cb_rows: host, concat of m_b row ids. */
+int twoace_solve_batch_codebook(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx,
+                                const int32_t* m, const int32_t* cb_rows, double row_scale,
+                                const double* B, const int32_t* train_idx, const twoace_params* params,
+                                double* X, double* Y, double* quality, double* info,
+                                double* stage_words);
+
+/* One InferADMM call per instance — inferLowRankV4.m:260-365 — exposed for per-stage parity tests.
+ *   X0     concat of n x r complex start points (same r for all instances)
+ *   X, Y   out: n x rout and m_b x rout per instance, rout = r if scale_by_row else 1
+ *   state  out or NULL: per instance final [X Z N (n x r each) | Y M (m_b x r each)] complex
+ *   words  out or NULL: nb x TWOACE_STAGE_WORDS
+ */
+int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const int32_t* m,
+                            const double* A, const double* B, int r, const double* X0,
+                            int scale_by_row, int use_rank_one, int nuclear,
+                            const twoace_params* params, double* X, double* Y, double* state,
+                            double* words);
+
+/* SpectralInitialize (inferLowRankV4.m:540-553) per instance: Xs out, nb x (n x r) complex. */
+int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m,
+                               const double* A, const double* B, int r, double* Xs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOACE_H */

@@ -27,6 +27,8 @@ struct twoace_ctx {
   DevBuf arena, ws, taskbuf;
   cd* cb_rm = nullptr;   // row-major codebook
   int cb_rows = 0, cb_n = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
 };
 
 #define CK(call)                                                                              \
@@ -173,8 +175,18 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
   const StageTask* dt = nullptr;
   rc = upload_tasks(ctx, tasks, cursor, &dt);
   if (rc) return rc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
   admm_stage_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), prm, dm, (cd*)ctx->ws.p);
   CK(cudaGetLastError());
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+  }
   ctx->launches++;
   return 0;
 }
@@ -791,5 +803,70 @@ extern "C" int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int 
   rc = launch_spectral(ctx, tasks, n, cursor); if (rc) return rc;
   rc = host_back(ctx, mem, Xs, dXs, (size_t)nb * n * r * sizeof(cd)); if (rc) return rc;
   if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_set_timing(twoace_ctx* ctx, int on) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->timing = on != 0;
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t* stage_launches) {
+  if (!ctx) return TWOACE_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for (auto& pr : ctx->stage_events) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (stage_ms) *stage_ms = tot;
+  if (stage_launches) *stage_launches = (int64_t)ctx->stage_events.size();
+  ctx->stage_events.clear();
+  return TWOACE_OK;
+}
+
+// 8 independent DFMA chains per thread, 2048 threads per SM: saturates the FP64 pipe.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int twoace_fp64_peak(twoace_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return TWOACE_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int blocks = ctx->num_sms * 8, iters = 4096;
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, (size_t)blocks * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    dfma_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 64.0 * iters * (double)blocks * 256.0;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
   return TWOACE_OK;
 }

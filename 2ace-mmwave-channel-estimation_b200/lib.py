@@ -20,7 +20,7 @@ EXPORTS = [
     "twoace_default_params", "twoace_version", "twoace_create", "twoace_destroy", "twoace_last_error",
     "twoace_stream", "twoace_launch_count", "twoace_synchronize", "twoace_solve_batch",
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
-    "twoace_spectral_init_batch",
+    "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
 ]
 
 
@@ -91,6 +91,12 @@ def load() -> C.CDLL:
     lib.twoace_infer_admm_batch.restype = C.c_int
     lib.twoace_spectral_init_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, dp, dp, C.c_int, dp]
     lib.twoace_spectral_init_batch.restype = C.c_int
+    lib.twoace_set_timing.argtypes = [vp, C.c_int]
+    lib.twoace_set_timing.restype = C.c_int
+    lib.twoace_timing_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.twoace_timing_collect.restype = C.c_int
+    lib.twoace_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.twoace_fp64_peak.restype = C.c_int
     _lib = lib
     return lib
 
@@ -144,6 +150,20 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.twoace_synchronize(self.h))
+
+    def set_timing(self, on: bool):
+        self.check(self.lib.twoace_set_timing(self.h, int(bool(on))))
+
+    def timing_collect(self):
+        """(summed stage-kernel ms, stage-kernel launches) since the last collect."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        self.check(self.lib.twoace_timing_collect(self.h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0.0)
+        self.check(self.lib.twoace_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     # ---- raw entry points (pointers may be NumPy arrays (host) or ints (device addresses)) ----
     def solve_batch_raw(self, variant, mem, nb, tx, rx, m, A, B, train_idx, params, X, Y, quality, info=None,

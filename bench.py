@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — ADMM CSI solves/sec (16x16 antennas, fixed iterations) on N B200s, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0]
+
+A "step" is one pass of the hot path over one batch of synthetic instances (the same batch every
+step; dense inputs of a batch exceed the 126 MB L2).  Workloads (BASELINE.json configs):
+  config1 (default)  inferLowRank_Nuclear, M in {32,64,128,256} x SNR in {0,10,20,30} dB
+  config0            inferLowRankV4_multi (what A2only dispatches to), M=64, SNR 20 dB
+Fixed-iteration mode: tol_rel = tol_abs = 0, maxiter = 500.
+N>1: launched under torchrun, one rank per GPU, trials sharded (weak scaling), max-over-ranks time,
+one NCCL all-reduce of the NMSE statistics tensor after the timed region.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ADMM CSI solves/sec (16x16 ant, fixed iters)"
+TX = RX = 16
+N = TX * RX
+
+WORKLOADS = {
+    "config1": dict(variant="NUCLEAR", Ms=[32, 64, 128, 256], snrs=[0.0, 10.0, 20.0, 30.0],
+                    desc="config1: inferLowRank_Nuclear, 16x16, M in {32,64,128,256} x SNR in {0,10,20,30} dB"),
+    "config0": dict(variant="V4_MULTI", Ms=[64], snrs=[20.0],
+                    desc="config0: inferLowRankV4_multi (A2only dispatch), 16x16, M=64, SNR 20 dB"),
+}
+
+
+def build_instances(wl, trials_per_cell, first_trial):
+    """trials_per_cell instances for every (M, SNR) cell; trial t of a cell uses SeedSequence child
+    first_trial + t, so the set is independent of the rank count."""
+    from twoace_b200 import harness as hz
+    cb = hz.load_codebook()
+    insts, cells = [], []
+    ci = 0
+    for M in wl["Ms"]:
+        for snr in wl["snrs"]:
+            batch = hz.make_batch(trials_per_cell, cb, M, snr, base_seed=hz.BASE_SEED + 7919 * ci,
+                                  first_trial=first_trial)
+            insts += batch
+            cells += [ci] * trials_per_cell
+            ci += 1
+    return insts, np.array(cells), ci
+
+
+def stage_flops(n, m, r, tx, nuclear):
+    """Algorithmic flops of one InferADMM iteration (SURVEY.md §8d contract figure, 8 flops per complex
+    MAC): min(explicit inverse, Woodbury) + ArgMinZ (V4: 16*tx*n*r; nuclear Gram-route SVT: 16*n*r^2)."""
+    core = min(8 * n * n * r + 24 * n * m * r, 24 * n * m * r + 8 * m * m * r)
+    return core + (16 * n * r * r if nuclear else 16 * tx * n * r)
+
+
+def solve_flops(insts, stage_words, variant, cc_frac=0.95, rmax=20):
+    """Sum over instances and stages of iterations actually executed x per-iteration flops."""
+    T = 3 if variant == "V4_MULTI" else 1
+    nuc = variant == "NUCLEAR"
+    tot = 0.0
+    for b, ins in enumerate(insts):
+        m = len(ins.B)
+        mtr = int(math.floor(m * cc_frac))
+        r = min(rmax, m, N)
+        sw = stage_words[b]
+        for s in range(4 * T):
+            tot += sw[s, 2] * stage_flops(N, mtr, r, TX, nuc)
+        tot += sw[4 * T, 2] * stage_flops(N, m, 1, TX, nuc)
+    return tot
+
+
+# ------------------------------------------------------------------------------- CPU oracle arm
+def _oracle_worker(job):
+    from threadpoolctl import threadpool_limits
+    from oracle import admm
+    variant, A, B, train_idx = job
+    p = admm.Params().fixed_iters()
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        if variant == "NUCLEAR":
+            X, _, _ = admm.infer_low_rank_nuclear(A, B, TX, RX, p, train_idx=train_idx[0])
+        elif variant == "V4_MULTI":
+            X, _, _ = admm.infer_low_rank_v4_multi(A, B, TX, RX, p, train_idx=train_idx[:3])
+        else:
+            X, _, _ = admm.infer_low_rank_v4(A, B, TX, RX, p, train_idx=train_idx[0])
+        dt = time.perf_counter() - t0
+    return X, dt
+
+
+def run_oracle_pool(variant, insts, cores):
+    """Time the NumPy oracle on `insts`, trial-parallel over `cores` single-threaded processes
+    (the analogue of the reference's parfor, Vs_M_par.m:145).  Returns (X list, wall seconds)."""
+    import multiprocessing as mp
+    jobs = [(variant, i.A, i.B, i.train_idx) for i in insts]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_noop, range(cores))            # start the workers (imports) outside the timed region
+        t0 = time.perf_counter()
+        out = pool.map(_oracle_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    return [o[0] for o in out], wall
+
+
+def _noop(_):
+    import numpy  # noqa: F401
+    from oracle import admm  # noqa: F401
+    return 0
+
+
+def sample_instances(insts, cells, n_cells, per_cell=1):
+    idx = []
+    for c in range(n_cells):
+        idx += list(np.nonzero(cells == c)[0][:per_cell])
+    return idx
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- main arms
+def reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_cells = len(wl["Ms"]) * len(wl["snrs"])
+    insts, cells, n_cells = build_instances(wl, max(1, math.ceil(cores / n_cells)), 0)
+    insts = [insts[i] for i in np.argsort(np.arange(len(insts)) % max(1, len(insts) // n_cells), kind="stable")]
+    per_step = max(1, min(len(insts), cores))
+    # a bounded sample per step: `per_step` instances cycling through the (M, SNR) cells
+    order = [insts[i % len(insts)] for i in range(per_step * (args.steps + args.warmup))]
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        pool.map(_noop, range(cores))
+        for s in range(args.warmup + args.steps):
+            jobs = [(wl["variant"], i.A, i.B, i.train_idx) for i in order[s * per_step:(s + 1) * per_step]]
+            t0 = time.perf_counter()
+            pool.map(_oracle_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = per_step / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step": per_step,
+                       "note": "NumPy oracle (port of the MATLAB path; MATLAB/Octave absent), one process per core"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} solves per step cycling through the workload's (M,SNR) cells"},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def ours_arm(args, wl, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, parallel as par
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = tw.Context(local_rank)
+    variant = getattr(tw, wl["variant"])
+    T = 3 if wl["variant"] == "V4_MULTI" else 1
+    tpc = args.trials_per_cell
+    insts, cells, n_cells = build_instances(wl, tpc, rank * tpc)   # weak scaling: tpc trials per cell per GPU
+    nb = len(insts)
+    p = tw.Params.default().fixed_iters()
+
+    m = np.array([len(i.B) for i in insts], dtype=np.int32)
+    A_h = np.concatenate([i.A.reshape(-1, order="F") for i in insts])
+    B_h = np.concatenate([i.B for i in insts])
+    tr_h = np.ascontiguousarray(np.concatenate([i.train_idx[:T].reshape(-1) for i in insts]).astype(np.int32))
+    sum_m = int(m.sum())
+    nstage = 4 * T + 1
+
+    # ---- device-resident inputs/outputs (the `value` leg)
+    A_d = torch.from_numpy(A_h.view(np.float64)).to(dev)
+    B_d = torch.from_numpy(B_h).to(dev)
+    X_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
+    Y_d = torch.empty(sum_m * 2, dtype=torch.float64, device=dev)
+    q_d = torch.empty(nb, dtype=torch.float64, device=dev)
+    info_d = torch.empty(nb * 16, dtype=torch.float64, device=dev)
+    sw_d = torch.empty(nb * nstage * 12, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.solve_batch_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, A_d.data_ptr(), B_d.data_ptr(), tr_h, p,
+                            X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), sw_d.data_ptr())
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    l0 = ctx.launch_count
+    ctx.set_timing(True)
+    ctx.timing_collect()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    stage_ms, stage_launches = ctx.timing_collect()
+    ctx.set_timing(False)
+    launches = ctx.launch_count - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = nb * world / (ms_step * 1e-3)
+
+    # ---- statistics reduce (the one collective of the path), outside the timed region
+    X = X_d.cpu().numpy().view(np.complex128).reshape(nb, N)
+    info = info_d.cpu().numpy().reshape(nb, 16)
+    sw = sw_d.cpu().numpy().reshape(nb, nstage, 12)
+    mse = np.array([hz.nmse(X[b], insts[b].vecH) for b in range(nb)])
+    stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info), dev if world > 1 else None)
+
+    # ---- roofline of the dominant kernel (admm_stage_kernel), live CUDA-event durations
+    flops_step = solve_flops(insts, sw, wl["variant"])
+    peak = ctx.fp64_peak_tflops()
+    achieved = flops_step * args.steps / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "kernel": "admm_stage_kernel", "kernel_ms_per_step": stage_ms / args.steps,
+                "kernel_launches_per_step": stage_launches / args.steps,
+                "kernel_share_of_step": stage_ms / ms_total,
+                "peak_source": "measured live: twoace_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 figure)",
+                "flops_per_step": flops_step}
+
+    # ---- end to end through the public C ABI with pinned HOST buffers (H2D + D2H inside the region)
+    A_p = torch.from_numpy(A_h.view(np.float64)).pin_memory()
+    B_p = torch.from_numpy(B_h).pin_memory()
+    X_p = torch.empty(nb * N * 2, dtype=torch.float64).pin_memory()
+    Y_p = torch.empty(sum_m * 2, dtype=torch.float64).pin_memory()
+    q_p = torch.empty(nb, dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def step_host():
+        ctx.solve_batch_raw(variant, tw.lib.MEM_HOST, nb, TX, RX, m, A_p.numpy(), B_p.numpy(), tr_h, p,
+                            X_p.numpy(), Y_p.numpy(), q_p.numpy(), None, None)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()          # synchronous: returns after the D2H copies have landed
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": nb * world / float(e2e_s.item()), "unit": "solves/s",
+           "h2d_bytes_per_step": int(A_p.numel() * 8 + B_p.numel() * 8 + tr_h.nbytes),
+           "d2h_bytes_per_step": int(X_p.numel() * 8 + Y_p.numel() * 8 + q_p.numel() * 8)}
+    e2e_match = float(np.max(np.abs(X_p.numpy() - X_d.cpu().numpy())))   # same kernels, same inputs
+
+    # ---- CPU baseline + NMSE delta on a bounded sample (rank 0, N=1 only)
+    cpu_baseline, nmse_delta = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sel = sample_instances(insts, cells, n_cells, per_cell=max(1, min(tpc, math.ceil(cores / n_cells))))
+        sub = [insts[i] for i in sel]
+        Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)))
+        cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": min(cores, len(sub)),
+                        "kind": "port",
+                        "sample": f"{len(sub)} of the step's {nb} instances ({len(sub) // n_cells} per (M,SNR) cell), "
+                                  f"NumPy oracle, 1 BLAS thread per process, {wall:.1f} s wall"}
+        g = hz.nmse_db([hz.nmse(X[i], insts[i].vecH) for i in sel])
+        o = hz.nmse_db([hz.nmse(Xo[k], sub[k].vecH) for k in range(len(sub))])
+        nmse_delta = g - o
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step_per_gpu": nb,
+                           "trials_per_cell_per_gpu": tpc, "cells": n_cells,
+                           "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step)",
+                           "mean_iters_per_solve": float(info[:, 15].mean())},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "nmse_delta_db": nmse_delta,
+                "nmse_db_per_cell": [None if not np.isfinite(v) else float(v) for v in par.nmse_db_per_cell(stats)],
+                "e2e_vs_device_max_abs_diff": e2e_match}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config1", choices=sorted(WORKLOADS))
+    ap.add_argument("--trials-per-cell", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.trials_per_cell is None:
+        args.trials_per_cell = 32 if args.workload == "config1" else 512
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import twoace_b200  # noqa: F401  (package import; fails loudly if the tree is broken)
+    if args.impl == "reference":
+        reference_arm(args, wl, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        ours_arm(args, wl, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,16 @@ int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, co
 int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m,
                                const double* A, const double* B, int r, double* Xs);
 
+/* Measurement hooks (bench.py).  With timing on, every InferADMM stage-kernel launch is bracketed by
+ * CUDA events on the context's stream; twoace_timing_collect synchronises, returns the summed
+ * duration (ms) and launch count since the last collect, and resets the accumulators. */
+int twoace_set_timing(twoace_ctx* ctx, int on);
+int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t* stage_launches);
+/* FP64 FMA throughput of this GPU (TFLOP/s, 2 flops per DFMA), measured with a register-resident
+ * DFMA loop: the roofline denominator of the FP64-pipe-bound stage kernel (MEASURED_PEAKS.json
+ * only carries HBM and bf16 figures). */
+int twoace_fp64_peak(twoace_ctx* ctx, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,276 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the NumPy oracle on identical seeded
+inputs and identical index sets.
+
+Tolerances (floating point, FP64 on both sides):
+  * per-stage iterate state after 1/2/10/100 iterations: relative Frobenius error <= 1e-9
+    (measured ~1e-14; the bar is loose only to stay robust across cuBLAS-free summation orders);
+  * full solves: per-instance relative error of the recovered CSI after global-phase alignment
+    (Evaluation_H.m:81-82) <= 1e-4 for >= 95 % of instances, quality to 1e-6,
+    integer bookkeeping (rank-one flag, roll-back flag, best trial, iteration counts, best
+    iteration / column) bit-exact on the instances that meet the bar;
+  * NMSE aggregated as 10*log10(mean) within 0.05 dB.
+
+Determinism note (see DESIGN.md "Parity regimes"): with tolerances forced to 0 and an
+under-determined instance (M=64 < 256 unknowns per column) the objective reaches ~1e-16 after
+~150 iterations, after which the reference's best-iterate / best-column / mu decisions compare
+rounding noise; any two implementations (including MATLAB on two machines) then return different
+interpolating solutions.  Per-instance parity is therefore asserted in the reference's default mode
+(tol_rel=1e-4, what every caller in the reference uses) and, for forced-iteration mode, on iterate
+state up to 100 iterations and on noisy well-determined instances.
+"""
+import numpy as np
+import pytest
+
+from oracle import admm
+
+pytestmark = pytest.mark.gpu
+
+TX = RX = 16
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def _stage_case(codebook, M, trial=0):
+    from twoace_b200 import harness as hz
+    ins = hz.make_batch(trial + 1, codebook, M, 20.0)[trial]
+    A, B, _, _ = admm._preprocess(ins.A, ins.B, 1e-8)
+    tr = ins.train_idx[0]
+    return A[tr], B[tr]
+
+
+@pytest.mark.parametrize("M", [36, 64, 121])
+def test_spectral_init_parity(codebook, gpu_ctx, M):
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, M)
+    r = min(20, At.shape[0])
+    Xo = admm.spectral_initialize(At, Bt, r)
+    Xg = sv.spectral_init_batch([At], [Bt], r, gpu_ctx)[0]
+    # the top-r eigenvectors are defined up to phase: compare the gauge-invariant X X'
+    assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-10
+
+
+def test_spectral_init_n_by_n_branch(codebook, gpu_ctx):
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, 361)     # m_train = 342 > n = 256
+    Xo = admm.spectral_initialize(At, Bt, 20)
+    Xg = sv.spectral_init_batch([At], [Bt], 20, gpu_ctx)[0]
+    assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-9
+
+
+@pytest.mark.parametrize("sbr,r,r1,nuc", [(True, 20, False, False), (False, 20, False, False),
+                                          (True, 1, True, False), (True, 20, True, False),
+                                          (True, 20, False, True), (False, 7, False, False)])
+@pytest.mark.parametrize("iters", [1, 2, 10, 100])
+def test_stage_state_parity(codebook, gpu_ctx, sbr, r, r1, nuc, iters):
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, 64)
+    X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
+    snap = {iters: None}
+    tro = admm.StageTrace()
+    zfn = admm.argmin_z_nuclear if nuc else admm.argmin_z
+    Xo, Yo, _ = admm.infer_admm(At, Bt, X0, sbr, r1, TX, RX, 0.0, 1e-3, 1.03, 0.0, 0.0, iters, None, None, zfn,
+                                tro, snap)
+    p = tw.Params.default(maxiter=iters, tol_rel=0.0, tol_abs=0.0)
+    Xg, Yg, Sg, W = sv.infer_admm_batch([At], [Bt], [X0], sbr, r1, TX, RX, p, nuclear=nuc, ctx=gpu_ctx)
+    s = snap[iters]
+    tol = 1e-9
+    assert rel(Sg[0]["X"], s["X"]) < tol
+    assert rel(Sg[0]["Z"], s["Z"]) < tol or np.linalg.norm(s["Z"]) < 1e-12
+    assert rel(Sg[0]["Y"], s["Y"]) < tol
+    # M and N can be pure rounding noise (exactly-satisfied constraints): compare absolutely
+    assert np.linalg.norm(Sg[0]["M"] - s["M"]) < tol * max(1.0, np.linalg.norm(s["M"]))
+    assert np.linalg.norm(Sg[0]["N"] - s["N"]) < tol * max(1.0, np.linalg.norm(s["N"]))
+    assert rel(Xg[0], Xo) < tol and rel(Yg[0], Yo) < tol
+    assert abs(W[0][0] - s["mu"]) <= 1e-12 * s["mu"]
+    assert int(W[0][2]) == iters
+    assert int(W[0][3]) == tro.opt_iter and int(W[0][4]) == tro.opt_col     # bit-exact bookkeeping
+    assert int(W[0][5]) == tro.n_mu_bumps
+
+
+@pytest.mark.parametrize("M", [36, 361])
+def test_stage_parity_other_shapes(codebook, gpu_ctx, M):
+    """M=36: K-split small-m path; M=361: explicit-inverse (non-Woodbury) branch."""
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, M)
+    X0 = admm.spectral_initialize(At, Bt, 20)
+    for iters in (1, 25):
+        snap = {iters: None}
+        admm.infer_admm(At, Bt, X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 0.0, 0.0, iters, None, None,
+                        admm.argmin_z, None, snap)
+        p = tw.Params.default(maxiter=iters, tol_rel=0.0, tol_abs=0.0)
+        _, _, Sg, _ = sv.infer_admm_batch([At], [Bt], [X0], True, False, TX, RX, p, ctx=gpu_ctx)
+        assert rel(Sg[0]["X"], snap[iters]["X"]) < 1e-9
+        assert rel(Sg[0]["Y"], snap[iters]["Y"]) < 1e-9
+
+
+def test_convergence_test_mode_matches_iteration_count(codebook, gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, 64)
+    X0 = admm.spectral_initialize(At, Bt, 20)
+    tro = admm.StageTrace()
+    Xo, Yo, conv = admm.infer_admm(At, Bt, X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 1e-4, 1e-8, 500, None, None,
+                                   admm.argmin_z, tro)
+    Xg, Yg, _, W = sv.infer_admm_batch([At], [Bt], [X0], True, False, TX, RX, tw.Params.default(), ctx=gpu_ctx)
+    assert int(W[0][2]) == tro.iters and bool(W[0][6]) == conv
+    assert rel(Xg[0], Xo) < 1e-9
+
+
+def _solve_both(variant, insts, p_gpu, p_or, ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    T = 3 if variant == tw.V4_MULTI else 1
+    res = sv.solve_batch(variant, [i.A for i in insts], [i.B for i in insts], TX, RX,
+                         [i.train_idx[:T] for i in insts], p_gpu, ctx)
+    fn = {tw.V4: admm.infer_low_rank_v4, tw.V4_MULTI: admm.infer_low_rank_v4_multi,
+          tw.NUCLEAR: admm.infer_low_rank_nuclear}[variant]
+    out = []
+    for ins in insts:
+        info = admm.SolveInfo()
+        tri = ins.train_idx[:3] if variant == tw.V4_MULTI else ins.train_idx[0]
+        Xo, Yo, qo = fn(ins.A, ins.B, TX, RX, p_or, train_idx=tri, info=info)
+        out.append((Xo, Yo, qo, info))
+    return res, out
+
+
+def _check_full(res, out, insts, frac=0.95, stage_exact=True):
+    from twoace_b200 import harness as hz
+    errs = np.array([hz.aligned_rel_err(res.X[b], out[b][0]) for b in range(len(insts))])
+    ok = errs <= 1e-4
+    assert ok.mean() >= frac, f"only {ok.mean():.2%} of instances within 1e-4: {errs}"
+    for b in np.nonzero(ok)[0]:
+        Xo, Yo, qo, info = out[b]
+        assert abs(res.quality[b] - qo) < 1e-6 or (np.isnan(qo) and np.isnan(res.quality[b]))
+        assert int(res.info[b, 2]) == int(info.used_rank_one)
+        assert int(res.info[b, 3]) == int(info.rolled_back)
+        assert int(res.info[b, 4]) == info.best_trial
+        assert res.Y[b].shape == Yo.shape
+        if stage_exact:
+            # per-stage iteration counts of the stages that ran, in launch order
+            ran = [int(w[2]) for w in res.stage_words[b] if w[2] > 0]
+            assert ran == [t.iters for t in info.traces]
+    nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in range(len(insts))])
+    nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in range(len(insts))])
+    assert abs(nm_g - nm_o) <= 0.05, (nm_g, nm_o)
+    return errs
+
+
+@pytest.mark.parametrize("variant_name", ["V4", "V4_MULTI", "NUCLEAR"])
+@pytest.mark.parametrize("M", [64, 225])
+def test_full_solve_parity_default_tolerances(codebook, gpu_ctx, variant_name, M):
+    """The reference's own operating mode (no caller passes more than 4 arguments)."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    variant = getattr(tw, variant_name)
+    n_inst = 12 if M == 64 else 6
+    insts = hz.make_batch(n_inst, codebook, M, 20.0)
+    res, out = _solve_both(variant, insts, tw.Params.default(), admm.Params(), gpu_ctx)
+    _check_full(res, out, insts)
+
+
+def test_full_solve_fixed_iterations_noisy_overdetermined(codebook, gpu_ctx):
+    """Forced-iteration mode on instances where the noise floor (SNR 10 dB, M=361) keeps every
+    decision away from rounding noise."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    insts = hz.make_batch(4, codebook, 361, 10.0)
+    p = tw.Params.default(maxiter=120).fixed_iters()
+    res, out = _solve_both(tw.V4, insts, p, admm.Params(maxiter=120).fixed_iters(), gpu_ctx)
+    _check_full(res, out, insts, frac=0.75)
+
+
+def test_nmse_statistics_fixed_iterations_config1(codebook, gpu_ctx):
+    """BASELINE config 1 (M=64, SNR 20 dB, 500 forced iterations): per-instance CSI is noise-determined
+    (see module docstring) but the reported NMSE must agree within 0.05 dB."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    insts = hz.make_batch(16, codebook, 64, 20.0)
+    res, out = _solve_both(tw.V4, insts, tw.Params.default().fixed_iters(), admm.Params().fixed_iters(), gpu_ctx)
+    nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in range(len(insts))])
+    nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in range(len(insts))])
+    assert abs(nm_g - nm_o) <= 0.05, (nm_g, nm_o)
+    # every stage ran exactly maxiter iterations
+    for b in range(len(insts)):
+        assert all(int(w[2]) in (0, 500) for w in res.stage_words[b])
+
+
+def test_known_answer_recipe_on_gpu(gpu_ctx):
+    """ADMM_v2.m:13-19,47-48 through the MATLAB-signature mirror."""
+    import twoace_b200 as tw
+    rng = np.random.default_rng(5)
+    T = 256
+    A = rng.standard_normal((T, 64)) + 1j * rng.standard_normal((T, 64))
+    Z = (rng.standard_normal((8, 2)) + 1j * rng.standard_normal((8, 2))) @ \
+        (rng.standard_normal((2, 8)) + 1j * rng.standard_normal((2, 8)))
+    Xgt = Z.reshape(-1, order="F")
+    B = np.abs(A @ Xgt)
+    tr = rng.permutation(T)[:243]
+    X, Y, q = tw.inferLowRankV4(A, B, 8, 8, train_idx=tr[None], ctx=gpu_ctx)
+    ratio = X / Xgt
+    assert np.linalg.norm(ratio - ratio.mean()) / np.linalg.norm(ratio) < 1e-4
+    assert q > 0.99
+    Xo, Yo, qo = admm.infer_low_rank_v4(A, B, 8, 8, train_idx=tr)
+    from twoace_b200 import harness as hz
+    assert hz.aligned_rel_err(X, Xo) < 1e-6
+    X3, _, q3 = tw.ADMM_v2(B, A, 8, 8, 3, tree="ns", train_idx=tr[None], ctx=gpu_ctx)
+    np.testing.assert_array_equal(X3, X)
+
+
+def test_codebook_mode_equals_dense_mode(codebook, gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    insts = hz.make_batch(4, codebook, 64, 20.0)
+    p = tw.Params.default()
+    d = sv.solve_batch(tw.V4, [i.A for i in insts], [i.B for i in insts], TX, RX, [i.train_idx[:1] for i in insts],
+                       p, gpu_ctx)
+    gpu_ctx.set_codebook(codebook)
+    c = sv.solve_batch_codebook(tw.V4, [i.rows for i in insts], 1.0 / 16, [i.B for i in insts], TX, RX,
+                                [i.train_idx[:1] for i in insts], p, gpu_ctx)
+    for b in range(4):
+        assert hz.aligned_rel_err(c.X[b], d.X[b]) < 1e-8
+        assert abs(c.quality[b] - d.quality[b]) < 1e-9
+    np.testing.assert_array_equal(c.info[:, 2:7], d.info[:, 2:7])
+
+
+def test_ragged_batch_equals_separate_solves(codebook, gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    Ms = [36, 121, 64, 9]
+    insts = [hz.make_batch(1, codebook, M, 20.0, base_seed=100 + M)[0] for M in Ms]
+    p = tw.Params.default(maxiter=80)
+    both = sv.solve_batch(tw.V4, [i.A for i in insts], [i.B for i in insts], TX, RX,
+                          [i.train_idx[:1] for i in insts], p, gpu_ctx)
+    for b, ins in enumerate(insts):
+        one = sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [ins.train_idx[:1]], p, gpu_ctx)
+        np.testing.assert_array_equal(one.X[0], both.X[b])       # same kernels, same order: bit-exact
+        np.testing.assert_array_equal(one.info[0], both.info[b])
+
+
+def test_degenerate_small_m_does_not_crash(codebook, gpu_ctx):
+    """M=4 (m_train=3 < r=4): zero spectral column -> Inf/NaN per-column rescale; NaN columns
+    never win (MATLAB min skips NaN) and the library must return without error."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    ins = hz.make_batch(1, codebook, 4, 20.0)[0]
+    res = sv.solve_batch(tw.V4_MULTI, [ins.A], [ins.B], TX, RX, [ins.train_idx], tw.Params.default(maxiter=50), gpu_ctx)
+    assert res.X.shape == (1, 256)
+    assert np.all(np.isfinite(res.X)) or np.all(np.isnan(res.X[0]))
+
+
+def test_error_reporting(codebook, gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    ins = hz.make_batch(1, codebook, 36, 20.0)[0]
+    bad = ins.train_idx[:1].copy()
+    bad[0, 0] = bad[0, 1]                                   # duplicate index
+    with pytest.raises(tw.TwoaceError, match="unique"):
+        sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [bad], None, gpu_ctx)
+    with pytest.raises(tw.TwoaceError, match="lambda"):
+        sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [ins.train_idx[:1]], tw.Params.default(lam=0.1), gpu_ctx)
+    # the context stays usable after an error
+    r = sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [ins.train_idx[:1]], tw.Params.default(maxiter=5), gpu_ctx)
+    assert r.X.shape == (1, 256)

@@ -27,6 +27,11 @@ struct twoace_ctx {
   DevBuf arena, ws, taskbuf;
   cd* cb_rm = nullptr;   // row-major codebook
   int cb_rows = 0, cb_n = 0;
+  uint32_t* cb_codes = nullptr;   // 2-bit codes of the codebook (n == 256 and quantised) or nullptr
+  double cb_mag = 0.0;
+  int opt_fast = 1;      // 1: use the shared-memory cluster kernel when a launch is eligible
+  int opt_fast_cs = 2;   // cluster size for the r = 20 stages (2 or 4)
+  int64_t fast_launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
 };
@@ -115,6 +120,7 @@ extern "C" void twoace_destroy(twoace_ctx* ctx) {
   if (ctx->ws.p) cudaFree(ctx->ws.p);
   if (ctx->taskbuf.p) cudaFree(ctx->taskbuf.p);
   if (ctx->cb_rm) cudaFree(ctx->cb_rm);
+  if (ctx->cb_codes) cudaFree(ctx->cb_codes);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -151,29 +157,94 @@ static int stage_grid(twoace_ctx* ctx, size_t smem, int ntasks, int* grid) {
   return 0;
 }
 
+template <int RL, int CS>
+static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const DevParams& prm, FastDims fd,
+                         bool* launched) {
+  *launched = false;
+  auto kern = fast_stage_kernel<RL, CS>;
+  const size_t smem = fast_smem_bytes<RL>(fd);
+  if (smem > 227 * 1024) return 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.gridDim = dim3((unsigned)(CS * ntasks), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int maxcl = 0;
+  CK(cudaOccupancyMaxActiveClusters(&maxcl, kern, &cfg));
+  if (maxcl < 1) return 0;
+  const int ncl = std::max(1, std::min(ntasks, maxcl));
+  fd.ws_stride = (fast_ws_elems(fd) + 15) / 16 * 16;
+  int rc = ensure(ctx, ctx->ws, (size_t)ncl * fd.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  cfg.gridDim = dim3((unsigned)(ncl * CS), 1, 1);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p));
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+  }
+  ctx->launches++;
+  ctx->fast_launches++;
+  *launched = true;
+  return 0;
+}
+
 static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
                         int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
   StageDims dm;
   dm.n = n; dm.tx = tx; dm.rx = rx; dm.maxm = 1; dm.maxr = 1; dm.dmax = 1;
-  bool nuc = false;
+  bool nuc = false, coded = true, same_r = true;
+  int minm = 1 << 30;
   for (const StageTask& t : tasks) {
     dm.maxm = std::max(dm.maxm, t.m);
+    minm = std::min(minm, t.m);
     dm.maxr = std::max(dm.maxr, t.r);
     dm.dmax = std::max(dm.dmax, use_woodbury(t.m, n) ? t.m : n);
     nuc = nuc || t.nuclear;
+    coded = coded && t.codes != nullptr && t.cscale != nullptr;
+    same_r = same_r && t.r == tasks[0].r;
+  }
+  const StageTask* dt = nullptr;
+  int rc = upload_tasks(ctx, tasks, cursor, &dt);
+  if (rc) return rc;
+  // ---- shared-memory cluster kernel: 16x16, quantised A, r in {20, 1}, m <= 256, V4 ArgMinZ
+  if (ctx->opt_fast && coded && same_r && !nuc && n == FN && tx == FTX && rx == FTX && dm.maxm <= 256 &&
+      (dm.maxr == 20 || dm.maxr == 1)) {
+    FastDims fd;
+    fd.maxm = dm.maxm; fd.mw = (dm.maxm + 15) / 16; fd.r = dm.maxr; fd.ws_stride = 0;
+    bool launched = false;
+    if (dm.maxr == 1) {
+      rc = launch_fast_t<1, 1>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
+    } else {
+      for (int attempt = 0; attempt < 2 && !launched && rc == 0; ++attempt) {
+        const int cs = (attempt == 0) ? ctx->opt_fast_cs : (ctx->opt_fast_cs == 2 ? 4 : 2);
+        if (cs == 2) rc = launch_fast_t<10, 2>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
+        else rc = launch_fast_t<5, 4>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
+      }
+    }
+    if (rc) return rc;
+    if (launched) return 0;
   }
   dm.ds = nuc ? std::max(tx, dm.maxr) : tx;
   if (dm.ds > SMALL_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "tx (or r for the nuclear variant) > %d", SMALL_DMAX);
   dm.ws_stride = (stage_ws_elems(dm) + 15) / 16 * 16;
   const size_t smem = stage_smem_bytes(dm);
   int grid = 0;
-  int rc = stage_grid(ctx, smem, (int)tasks.size(), &grid);
+  rc = stage_grid(ctx, smem, (int)tasks.size(), &grid);
   if (rc) return rc;
   rc = ensure(ctx, ctx->ws, (size_t)grid * dm.ws_stride * sizeof(cd));
-  if (rc) return rc;
-  const StageTask* dt = nullptr;
-  rc = upload_tasks(ctx, tasks, cursor, &dt);
   if (rc) return rc;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
@@ -358,6 +429,9 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   const size_t o_ymax = bp.take(b_off[nb] * sizeof(cd));
   const size_t o_yr = bp.take(b_off[nb] * sizeof(cd));
   const size_t o_sw = bp.take((size_t)nb * nstage * STAGE_SCAL * sizeof(double));
+  const bool try_codes = ctx->opt_fast && n == FN && in.tx == FTX && in.rx == FTX;
+  const size_t o_codes = (dense && try_codes) ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
+  const size_t o_qflag = (dense && try_codes) ? bp.take((size_t)nb * sizeof(int)) : 0;
   int rc = ensure(ctx, ctx->arena, bp.off + 256);
   if (rc) return rc;
   char* base = (char*)ctx->arena.p;
@@ -381,7 +455,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   CK(cudaMemsetAsync(d_sw, 0, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), ctx->stream));
 
   // task buffer: generous upper bound for all task arrays of this chunk
-  const size_t task_bytes = (size_t)nb * (sizeof(PrepTask) + T * (sizeof(SpecTask) + 4 * sizeof(StageTask) +
+  const size_t task_bytes = (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + T * (sizeof(SpecTask) + 4 * sizeof(StageTask) +
                             2 * sizeof(OrthoTask) + 2 * sizeof(QualTask)) + sizeof(StageTask) + sizeof(FinalTask)) +
                             256 * (8 * T + 8);
   rc = ensure(ctx, ctx->taskbuf, task_bytes);
@@ -389,6 +463,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   size_t cursor = 0;
   const DevParams prm = make_dev_params(in.p);
   const cd* Abase_all = dense ? d_Arm : ctx->cb_rm;
+  bool use_codes = false;
 
   // ---- pre-processing
   {
@@ -399,6 +474,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       t.A_rm = dense ? d_Arm + a_off[b] : nullptr;
       t.cb = ctx->cb_rm; t.cbrows = dense ? nullptr : d_fullA + b_off[b];
       t.row_scale = in.row_scale; t.B = in.dB + b_off[b]; t.m = in.m[b]; t.ctl = d_ctl + b;
+      t.code_mag = dense ? 0.0 : ctx->cb_mag;
     }
     const PrepTask* dt = nullptr;
     rc = upload_tasks(ctx, pt, cursor, &dt);
@@ -406,6 +482,27 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
     prep_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dt, nb, n, in.p.tol_abs);
     CK(cudaGetLastError());
     ctx->launches++;
+    if (dense && try_codes) {   // 2-bit phase codes of every instance's A; all-or-nothing per chunk
+      std::vector<QuantTask> qt(nb);
+      for (int b = 0; b < nb; ++b) {
+        QuantTask& q = qt[b];
+        q.A_rm = d_Arm + a_off[b]; q.rows = in.m[b]; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * 16;
+        q.mag_out = nullptr; q.flag_out = (int*)(base + o_qflag) + b; q.ctl = d_ctl + b;
+      }
+      const QuantTask* dq = nullptr;
+      rc = upload_tasks(ctx, qt, cursor, &dq);
+      if (rc) return rc;
+      quant_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dq, nb);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      std::vector<int> flags(nb);
+      CK(cudaMemcpyAsync(flags.data(), base + o_qflag, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      use_codes = true;
+      for (int b = 0; b < nb; ++b) use_codes = use_codes && flags[b] == 1;
+    } else if (!dense && try_codes) {
+      use_codes = ctx->cb_codes != nullptr;
+    }
     fill_nan_kernel<<<std::min(4 * ctx->num_sms, (int)(((size_t)nb * n + 255) / 256)), 256, 0, ctx->stream>>>(d_xmax, (size_t)nb * n);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -446,6 +543,8 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.sbr = 1; a.rank_one = pass; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
         a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
+        a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
+        a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
         StageTask& s2 = sb[b];
         s2 = a;
         s2.X0 = d_Xa + (size_t)b * xstride; s2.Xout = d_xb + (size_t)b * n; s2.Yout = d_yb + b_off[b];
@@ -486,6 +585,8 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.sbr = 1; a.rank_one = 0; a.nuclear = nuclear; a.rank_one_ptr = &d_ctl[b].use_rank_one;
       a.active = nullptr; a.active_expect = 1;
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
+      a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
+      a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
       FinalTask& f = ft[b];
       f.x0 = d_xmax + (size_t)b * n; f.y0 = d_ymax + b_off[b]; f.xr = d_xr + (size_t)b * n; f.yr = d_yr + b_off[b];
       f.m = in.m[b]; f.mtr = mtr[b]; f.Xout = in.dX + (size_t)b * n; f.Yout = in.dY + b_off[b];
@@ -651,6 +752,26 @@ extern "C" int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, co
   ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->cb_rows = rows; ctx->cb_n = n;
+  if (ctx->cb_codes) { CK(cudaFree(ctx->cb_codes)); ctx->cb_codes = nullptr; }
+  ctx->cb_mag = 0.0;
+  if (n == FN) {   // try the 2-bit representation (every shipped codebook qualifies)
+    uint32_t* codes = nullptr;
+    CK(cudaMalloc((void**)&codes, (size_t)rows * 16 * sizeof(uint32_t) + 64));
+    char* aux = nullptr;
+    CK(cudaMalloc((void**)&aux, 64 + sizeof(QuantTask)));
+    QuantTask q;
+    q.A_rm = ctx->cb_rm; q.rows = rows; q.codes = codes; q.mag_out = (double*)aux; q.flag_out = (int*)(aux + 8); q.ctl = nullptr;
+    CK(cudaMemcpyAsync(aux + 64, &q, sizeof q, cudaMemcpyHostToDevice, ctx->stream));
+    quant_kernel<<<1, NT, 0, ctx->stream>>>((const QuantTask*)(aux + 64), 1);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    struct { double mag; int flag; int pad; } res;
+    CK(cudaMemcpyAsync(&res, aux, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(aux));
+    if (res.flag == 1) { ctx->cb_codes = codes; ctx->cb_mag = res.mag; }
+    else CK(cudaFree(codes));
+  }
   return TWOACE_OK;
 }
 
@@ -701,12 +822,16 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
   Bump bp;
   const size_t o_Arm = bp.take(a_off[nb] * sizeof(cd)), o_one = bp.take(sizeof(double));
   const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
+  const bool try_codes = ctx->opt_fast && n == FN && tx == FTX && rx == FTX && !nuclear && (r == 20 || r == 1);
+  const size_t o_codes = try_codes ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
+  const size_t o_qflag = try_codes ? bp.take((size_t)nb * sizeof(int)) : 0;
+  const size_t o_mag = try_codes ? bp.take((size_t)nb * sizeof(double)) : 0;
   rc = ensure(ctx, ctx->arena, bp.off + 256); if (rc) return rc;
   char* base = (char*)ctx->arena.p;
   cd* d_Arm = (cd*)(base + o_Arm);
   double* d_one = (double*)(base + o_one);
   InstCtl* d_ctl = (InstCtl*)(base + o_ctl);
-  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(StageTask)) + 4096); if (rc) return rc;
+  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + sizeof(StageTask)) + 4096); if (rc) return rc;
   size_t cursor = 0;
   set_ones_kernel<<<1, 32, 0, ctx->stream>>>(d_one, 1);
   CK(cudaGetLastError());
@@ -724,9 +849,30 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     CK(cudaGetLastError());
     ctx->launches++;
   }
+  bool use_codes = false;
+  if (try_codes) {
+    std::vector<QuantTask> qt(nb);
+    for (int b = 0; b < nb; ++b) {
+      QuantTask& q = qt[b];
+      q.A_rm = d_Arm + a_off[b]; q.rows = m[b]; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * 16;
+      q.mag_out = (double*)(base + o_mag) + b; q.flag_out = (int*)(base + o_qflag) + b; q.ctl = nullptr;
+    }
+    const QuantTask* dq = nullptr;
+    rc = upload_tasks(ctx, qt, cursor, &dq); if (rc) return rc;
+    quant_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dq, nb);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    std::vector<int> flags(nb);
+    CK(cudaMemcpyAsync(flags.data(), base + o_qflag, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    use_codes = true;
+    for (int b = 0; b < nb; ++b) use_codes = use_codes && flags[b] == 1;
+  }
   std::vector<StageTask> tasks(nb);
   for (int b = 0; b < nb; ++b) {
     StageTask& a = tasks[b];
+    a.codes = use_codes ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : nullptr;
+    a.cscale = use_codes ? (const double*)(base + o_mag) + b : nullptr;
     a.A.base = d_Arm + a_off[b]; a.A.rows = nullptr; a.A.scale = d_one;
     a.B = (const double*)dB + b_off[b]; a.brows = nullptr; a.bscale = d_one;
     a.m = m[b]; a.r = r; a.X0 = (const cd*)dX0 + (size_t)b * n * r;
@@ -870,3 +1016,16 @@ extern "C" int twoace_fp64_peak(twoace_ctx* ctx, double* tflops) {
   *tflops = best;
   return TWOACE_OK;
 }
+
+extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  const std::string k(key);
+  if (k == "fast") ctx->opt_fast = value ? 1 : 0;
+  else if (k == "fast_cs") { if (value != 2 && value != 4) FAIL(TWOACE_E_INVALID, "fast_cs must be 2 or 4"); ctx->opt_fast_cs = value; }
+  else if (k == "chunk") { if (value < 1) FAIL(TWOACE_E_INVALID, "chunk must be >= 1"); ctx->chunk = value; }
+  else FAIL(TWOACE_E_INVALID, "unknown option %s", key);
+  return TWOACE_OK;
+}
+
+extern "C" int64_t twoace_fast_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->fast_launches : 0; }

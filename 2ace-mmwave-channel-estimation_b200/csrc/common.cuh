@@ -104,14 +104,30 @@ __device__ __forceinline__ void rr_pair(int d2, int round, int k, int& p, int& q
   if (p > q) { int t = p; p = q; q = t; }
 }
 
+// Rotation J = [[c, s],[-s e, c e]] (e = e^{-i theta}) that annihilates the (p,q) entry of the Hermitian
+// 2x2 block [[a, b],[conj b, cc]].  Returns false (identity) when |b| is negligible.
+__device__ __forceinline__ bool jacobi_rot(double a, double cc, cd b, double floor2, double& c, double& s, cd& e) {
+  const double ab2 = cabs2(b);
+  c = 1.0; s = 0.0; e = cmk(1.0, 0.0);
+  if (!(ab2 > floor2) || !(ab2 > 1.0e-34 * fabs(a * cc)) || !(ab2 > 1e-300)) return false;
+  // rsqrt / rcp (1 ulp) keep the dependent chain short; J stays unitary to ~1 ulp
+  const double rab = rsqrt(ab2);
+  const double tau = 0.5 * (cc - a) * rab;
+  const double x1 = fma(tau, tau, 1.0);
+  const double w = x1 * rsqrt(x1);
+  const double t = copysign(__drcp_rn(fabs(tau) + w), tau);
+  c = rsqrt(fma(t, t, 1.0));
+  s = t * c;
+  e = cmk(b.x * rab, -b.y * rab);
+  return true;
+}
+
 __device__ inline int jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, bool init_v,
                                   JacobiScratch js, int max_sweeps = 40) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (init_v) {
-    for (int idx = tid; idx < d * d; idx += NT) {
-      int i = idx % d, j = idx / d;
-      V[i + (size_t)ldv * j] = cmk(i == j ? 1.0 : 0.0, 0.0);
-    }
+    for (int j = warp; j < d; j += NW)
+      for (int i = lane; i < d; i += 32) V[i + (size_t)ldv * j] = cmk(i == j ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
   if (d < 2) return 0;
@@ -125,80 +141,153 @@ __device__ inline int jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, bool in
   }
   __syncthreads();
   const double floor_abs = 1.0e-18 * (*js.gscale);
+  const double floor2 = floor_abs * floor_abs;
+  // the pair of (round, k) is packed as (p << 16) | q in the low bits of js.cs-adjacent storage: we keep
+  // it in registers of the d2 parameter threads and publish it through js.sn/js.cs companions below
   int sweeps = 0;
   for (; sweeps < max_sweeps; ++sweeps) {
     if (tid == 0) *js.flag = 0;
     __syncthreads();
     for (int rd = 0; rd < rounds; ++rd) {
-      // --- rotation parameters
-      if (tid < d2) {
+      // --- rotation parameters (one thread per pair); the pair indices ride along in e.y of a 2nd slot
+      for (int k = tid; k < d2; k += NT) {
         int p, q;
-        rr_pair(d2, rd, tid, p, q);
+        rr_pair(d2, rd, k, p, q);
         double c = 1.0, s = 0.0;
         cd e = cmk(1.0, 0.0);
         if (q < d) {
-          cd b = G[p + (size_t)ldg * q];
-          double a = G[p + (size_t)ldg * p].x, cc = G[q + (size_t)ldg * q].x;
-          double ab = sqrt(cabs2(b));
-          // rotate unless the off-diagonal is negligible against the diagonal pair
-          if (ab > floor_abs && ab > 1.0e-17 * sqrt(fabs(a) * fabs(cc)) && ab > 1e-300) {
-            double tau = (cc - a) / (2.0 * ab);
-            double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = t * c;
-            e = cmk(b.x / ab, -b.y / ab);  // e^{-i theta}
-            *js.flag = 1;
-          }
+          const cd b = G[p + (size_t)ldg * q];
+          const double a = G[p + (size_t)ldg * p].x, cc = G[q + (size_t)ldg * q].x;
+          if (jacobi_rot(a, cc, b, floor2, c, s, e)) *js.flag = 1;
         }
-        js.cs[tid] = c;
-        js.sn[tid] = s;
-        js.e[tid] = e;
+        js.cs[k] = c;
+        js.sn[k] = s;
+        js.e[k] = e;
       }
       __syncthreads();
-      // --- column update of G and V:  [gp gq] <- [gp gq] * J,  J = [[c, s],[-s e, c e]]
-      for (int idx = tid; idx < 2 * d2 * d; idx += NT) {
-        int which = idx / (d2 * d);
-        int rem = idx - which * (d2 * d);
-        int k = rem / d, i = rem - k * d;
-        double s = js.sn[k];
+      // --- column update of G and V:  [gp gq] <- [gp gq] * J   (warp per pair, lanes over rows)
+      for (int k = warp; k < d2; k += NW) {
+        const double s = js.sn[k];
         if (s == 0.0) continue;
         int p, q;
         rr_pair(d2, rd, k, p, q);
-        double c = js.cs[k];
-        cd e = js.e[k];
-        cd* Mx = which ? V : G;
-        int ld = which ? ldv : ldg;
-        cd gp = Mx[i + (size_t)ld * p], gq = Mx[i + (size_t)ld * q];
-        cd eq = cmul(e, gq);
-        Mx[i + (size_t)ld * p] = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
-        Mx[i + (size_t)ld * q] = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
+        const double c = js.cs[k];
+        const cd e = js.e[k];
+        for (int i = lane; i < 2 * d; i += 32) {
+          cd* Mx = (i < d) ? G : V;
+          const int ld = (i < d) ? ldg : ldv;
+          const int ii = (i < d) ? i : i - d;
+          const cd gp = Mx[ii + (size_t)ld * p], gq = Mx[ii + (size_t)ld * q];
+          const cd eq = cmul(e, gq);
+          Mx[ii + (size_t)ld * p] = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
+          Mx[ii + (size_t)ld * q] = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
+        }
       }
       __syncthreads();
       // --- row update of G:  [gp; gq] <- J' * [gp; gq]
-      for (int idx = tid; idx < d2 * d; idx += NT) {
-        int k = idx / d, j = idx - k * d;
-        double s = js.sn[k];
+      for (int k = warp; k < d2; k += NW) {
+        const double s = js.sn[k];
         if (s == 0.0) continue;
         int p, q;
         rr_pair(d2, rd, k, p, q);
-        double c = js.cs[k];
-        cd ec = cconj(js.e[k]);
-        cd gp = G[p + (size_t)ldg * j], gq = G[q + (size_t)ldg * j];
-        cd eq = cmul(ec, gq);
-        cd np_ = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
-        cd nq_ = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
-        if (j == p) np_.y = 0.0;
-        if (j == q) nq_.y = 0.0;
-        if (j == q) np_ = cmk(0.0, 0.0);   // annihilated element (exactly)
-        if (j == p) nq_ = cmk(0.0, 0.0);
-        G[p + (size_t)ldg * j] = np_;
-        G[q + (size_t)ldg * j] = nq_;
+        const double c = js.cs[k];
+        const cd ec = cconj(js.e[k]);
+        for (int j = lane; j < d; j += 32) {
+          const cd gp = G[p + (size_t)ldg * j], gq = G[q + (size_t)ldg * j];
+          const cd eq = cmul(ec, gq);
+          cd np_ = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
+          cd nq_ = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
+          if (j == p) np_.y = 0.0;
+          if (j == q) nq_.y = 0.0;
+          if (j == q) np_ = cmk(0.0, 0.0);   // annihilated element (exactly)
+          if (j == p) nq_ = cmk(0.0, 0.0);
+          G[p + (size_t)ldg * j] = np_;
+          G[q + (size_t)ldg * j] = nq_;
+        }
       }
       __syncthreads();
     }
     int f = *js.flag;
     __syncthreads();
     if (!f) break;
+  }
+  return sweeps;
+}
+
+// ------------------------------------------------------------------------------------------
+// 16 x 16 specialisation for the ArgMinZ eigenproblem of the shared-memory kernel (exactly NT = 256
+// threads).  Two-sided Jacobi, double-buffered (column update G -> H, row update H -> G) so that each
+// round needs two barriers; every thread derives the rotation of its own pair redundantly from G, the
+// pair table `pairs` ([15][8][2] bytes) is precomputed.  V is updated in place; with init_v == false the
+// caller supplies V and the already rotated G = V' G0 V (warm start).
+__device__ __forceinline__ void jacobi16_pairs(unsigned char* pairs) {
+  for (int idx = threadIdx.x; idx < 15 * 8; idx += NT) {
+    int p, q;
+    rr_pair(8, idx >> 3, idx & 7, p, q);
+    pairs[2 * idx] = (unsigned char)p;
+    pairs[2 * idx + 1] = (unsigned char)q;
+  }
+}
+
+__device__ inline int jacobi16(cd* G, cd* H, cd* V, const unsigned char* pairs, double* prm, bool init_v,
+                               int max_sweeps = 30) {
+  const int tid = threadIdx.x;
+  const int which = tid >> 7, k = (tid >> 4) & 7, i = tid & 15;
+  const int leader = tid & 16;   // lane (within the warp) of the first thread of this half-warp
+  if (init_v) V[tid] = cmk((i == (tid >> 4)) ? 1.0 : 0.0, 0.0);
+  double g = 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) g = fmax(g, fabs(G[17 * q].x));
+  const double floor_abs = 1.0e-18 * g;
+  const double floor2 = floor_abs * floor_abs;
+  __syncthreads();
+  cd* Mx = which ? V : G;
+  cd* Mo = which ? V : H;
+  int sweeps = 0;
+  for (; sweeps < max_sweeps;) {
+    double smax = 0.0;
+    for (int rd = 0; rd < 15; ++rd) {
+      const int p = pairs[2 * (rd * 8 + k)], q = pairs[2 * (rd * 8 + k) + 1];
+      double c = 1.0, s = 0.0;
+      cd e = cmk(1.0, 0.0);
+      if (i == 0) {   // one thread per half-warp derives the rotation, the other 15 receive it
+        jacobi_rot(G[17 * p].x, G[17 * q].x, G[p + 16 * q], floor2, c, s, e);
+        smax = fmax(smax, fabs(s));
+      }
+      c = __shfl_sync(0xffffffffu, c, leader);
+      s = __shfl_sync(0xffffffffu, s, leader);
+      e.x = __shfl_sync(0xffffffffu, e.x, leader);
+      e.y = __shfl_sync(0xffffffffu, e.y, leader);
+      {
+        const cd gp = Mx[i + 16 * p], gq = Mx[i + 16 * q];
+        const cd eq = cmul(e, gq);
+        Mo[i + 16 * p] = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
+        Mo[i + 16 * q] = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
+      }
+      if (tid < 128 && i == 0) { prm[4 * k] = c; prm[4 * k + 1] = s; prm[4 * k + 2] = e.x; prm[4 * k + 3] = e.y; }
+      __syncthreads();
+      if (tid < 128) {   // row update H -> G, item (pair k, column j = i)
+        const double c2 = prm[4 * k], s2 = prm[4 * k + 1];
+        const cd ec = cmk(prm[4 * k + 2], -prm[4 * k + 3]);
+        const cd hp = H[p + 16 * i], hq = H[q + 16 * i];
+        const cd eq = cmul(ec, hq);
+        cd np_ = cmk(c2 * hp.x - s2 * eq.x, c2 * hp.y - s2 * eq.y);
+        cd nq_ = cmk(s2 * hp.x + c2 * eq.x, s2 * hp.y + c2 * eq.y);
+        if (s2 != 0.0) {
+          if (i == p) np_.y = 0.0;
+          if (i == q) nq_.y = 0.0;
+          if (i == q) np_ = cmk(0.0, 0.0);
+          if (i == p) nq_ = cmk(0.0, 0.0);
+        }
+        G[p + 16 * i] = np_;
+        G[q + 16 * i] = nq_;
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    // quadratic convergence: a sweep whose largest rotation had |sin| <= 1e-8 leaves off-diagonals at the
+    // 1e-16 level, so no verification sweep is needed
+    if (!__syncthreads_or(smax > 1.0e-8)) break;
   }
   return sweeps;
 }

@@ -1,0 +1,836 @@
+// Fast InferADMM kernel for the 16x16 (n = 256) quantised-codebook case: the whole iterate lives in
+// shared memory and the r columns of X are split over a thread-block cluster (CS CTAs, RL = r/CS
+// columns each).  Cross-CTA coupling is only
+//   * the row norms of A X + M/mu (scale_by_row),
+//   * the tx x tx Gram E E' of ArgMinZ,
+//   * a handful of residual norms / per-column objectives,
+// exchanged through distributed shared memory; the A-products are fully local.
+//
+// The sensing matrix is held as 2-bit phase codes: every shipped codebook entry is a 4th root of
+// unity, A_eff = cscale * u, u in {1, j, -1, -j}; two packed copies ([i-word][k] and
+// [k-word][i], 16 codes per 32-bit word) serve the A'(.) and A(.) products without a transpose.
+// Same algorithm as admm_stage.cuh (inferLowRankV4.m:260-365); differences, exact in exact arithmetic:
+//   * Woodbury form of ArgMinX (S = I + A A' from exact integer phase counts, S^-1 streamed from L2);
+//   * N is overwritten by Z_in = X + N/mu during ArgMinZ and rebuilt as N = mu (Z_in - Z)
+//     (identical to N + mu (X - Z), :319-320);
+//   * A'Y (:309) lives in global memory and is advanced by A'(Y - Y0), only when a tolerance is set;
+//   * the best iterate (:323-340) is written straight to the output buffers.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "admm_stage.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace twoace {
+
+constexpr int FN = 256;    // n
+constexpr int FTX = 16;    // tx (= rx)
+constexpr int XS_SCAL = 16;
+
+struct FastDims {
+  int maxm;          // largest m in the launch
+  int mw;            // ceil(maxm/16): words per k of the [i-word][k] code copy
+  int r;             // total columns (CS * RL)
+  size_t ws_stride;  // global workspace elements (cd) per cluster
+};
+
+__host__ __device__ inline size_t fast_ws_elems(const FastDims& d) {
+  return (size_t)d.maxm * d.maxm + (size_t)FN * d.r;   // Sinv | AtY
+}
+
+template <int RL>
+__host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
+  size_t b = 0;
+  b += 3 * (size_t)FN * RL * sizeof(cd);                    // X Z N
+  b += 4 * (size_t)d.maxm * RL * sizeof(cd);                // Y M WT AX
+  b += 4 * (size_t)FTX * FTX * sizeof(cd);                  // G U P xG
+  b += 8 * sizeof(cd) + 256 + 32 * sizeof(double);          // LUTs, Jacobi pair table + rotation params
+  b += (size_t)(FTX / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
+  b += (size_t)d.maxm * sizeof(double) * 5;                 // Bs, xrow[2], rowtot[2]
+  b += (2 * XS_SCAL + 2 * SMALL_DMAX) * sizeof(double);     // xsc (double-buffered), xcol (double-buffered)
+  b += (16 * NW + FTX + SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
+  b += (size_t)d.mw * 256 * 4 + (size_t)16 * d.maxm * 4;    // cki, cik
+  b += (size_t)d.maxm * sizeof(int) + 16 * sizeof(int);
+  return b + 256;
+}
+
+template <int RL>
+struct FastSmem {
+  cd *X, *Z, *N, *Y, *M, *WT, *AX, *G, *U, *P;
+  cd* xG;           // exchange: Gram partial
+  cd* lut;          // [0..3] u(code), [4..7] conj(u(code))
+  JacobiScratch js;
+  unsigned char* pairs;   // [15][8][2] round-robin pair table of jacobi16
+  double* jprm;           // [8][4] rotation parameters of the current round
+  double* Bs;
+  double* xrow;     // exchange: [2*maxm] row partial sums
+  double* rowtot;   // [2*maxm] cluster totals
+  double* xsc;      // exchange: [2][XS_SCAL] scalars (parity double-buffered)
+  double* xcol;     // exchange: [2][SMALL_DMAX] per-column objectives (owner writes its slots)
+  double *red, *s2s, *colsc, *sc;
+  uint32_t* cki;    // [mw][256]   code(i = 16w + j, k) in bits 2j of cki[w*256 + k]
+  uint32_t* cik;    // [16][m]     code(i, k = 16w + j) in bits 2j of cik[w*m + i]
+  int* rows_s;
+  int* ifl;
+};
+
+template <int RL>
+__device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
+  FastSmem<RL> s;
+  s.X = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
+  s.Z = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
+  s.N = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
+  s.Y = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
+  s.M = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
+  s.WT = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
+  s.AX = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
+  s.G = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
+  s.P = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
+  s.U = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);    // persistent across iterations (warm start)
+  s.xG = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
+  s.pairs = (unsigned char*)p; p += 256;
+  s.jprm = (double*)p; p += 32 * sizeof(double);
+  s.lut = (cd*)p; p += 8 * sizeof(cd);
+  const int h = FTX / 2 + 2;
+  s.js.e = (cd*)p; p += (size_t)h * sizeof(cd);
+  s.js.cs = (double*)p; p += (size_t)h * sizeof(double);
+  s.js.sn = (double*)p; p += (size_t)h * sizeof(double);
+  s.Bs = (double*)p; p += (size_t)d.maxm * sizeof(double);
+  s.xrow = (double*)p; p += (size_t)2 * d.maxm * sizeof(double);
+  s.rowtot = (double*)p; p += (size_t)2 * d.maxm * sizeof(double);
+  s.xsc = (double*)p; p += 2 * XS_SCAL * sizeof(double);
+  s.xcol = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
+  s.red = (double*)p; p += 16 * NW * sizeof(double);
+  s.s2s = (double*)p; p += FTX * sizeof(double);
+  s.colsc = (double*)p; p += SMALL_DMAX * sizeof(double);
+  s.sc = (double*)p; p += 32 * sizeof(double);
+  s.cki = (uint32_t*)p; p += (size_t)d.mw * 256 * 4;
+  s.cik = (uint32_t*)p; p += (size_t)16 * d.maxm * 4;
+  s.rows_s = (int*)p; p += (size_t)d.maxm * sizeof(int);
+  s.ifl = (int*)p; p += 16 * sizeof(int);
+  s.js.flag = s.ifl + 8;
+  s.js.gscale = s.sc + 31;
+  return s;
+}
+
+template <int CS>
+__device__ __forceinline__ void cl_sync() {
+  if constexpr (CS > 1) cg::this_cluster().sync();
+  else __syncthreads();
+}
+
+template <class T, int CS>
+__device__ __forceinline__ T* peer_ptr(T* p, int rank) {
+  if constexpr (CS > 1) return cg::this_cluster().map_shared_rank(p, rank);
+  else return p;
+}
+
+// acc[c] += sum_i conj(u(i,k)) * Op[i + ldo*c]   for this thread's k (A' product, one thread per k)
+template <int RL>
+__device__ __forceinline__ void prod_ah(const uint32_t* cki, int m, const cd* Op, int ldo, const cd* lutc,
+                                        cd (&acc)[RL]) {
+  const int k = threadIdx.x;
+  for (int w = 0; w * 16 < m; ++w) {
+    uint32_t word = cki[w * 256 + k];
+    const int cnt = min(16, m - w * 16);
+    const cd* op = Op + w * 16;
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const cd a = lutc[word & 3u];
+      word >>= 2;
+#pragma unroll
+      for (int c = 0; c < RL; ++c) cfma(acc[c], a, op[j + ldo * c]);
+    }
+  }
+}
+
+// store(i, c, sum_k u(i,k) * V[k + 256*c]); the k range is split over thread groups when m is small
+template <int RL, class StoreF>
+__device__ __forceinline__ void prod_a(const uint32_t* cik, int m, const cd* V, const cd* lut, cd* scratch,
+                                       size_t scratch_cap, StoreF store) {
+  const int tid = threadIdx.x;
+  int ks = 1;
+  while (ks < 16 && 2 * ks * m <= NT && (size_t)(2 * ks) * m * RL <= scratch_cap) ks *= 2;
+  const int i = tid % m, s = tid / m;
+  const bool act = s < ks;
+  cd acc[RL];
+#pragma unroll
+  for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+  if (act) {
+    const int wper = 16 / ks;
+    for (int w = s * wper; w < (s + 1) * wper; ++w) {
+      uint32_t word = cik[w * m + i];
+      const cd* v = V + w * 16;
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const cd a = lut[word & 3u];
+        word >>= 2;
+#pragma unroll
+        for (int c = 0; c < RL; ++c) cfma(acc[c], a, v[j + FN * c]);
+      }
+    }
+  }
+  __syncthreads();   // scratch may alias buffers other threads were still reading
+  if (ks > 1) {
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < RL; ++c) scratch[((size_t)s * m + i) * RL + c] = acc[c];
+    }
+    __syncthreads();
+    if (act && s == 0) {
+      for (int t = 1; t < ks; ++t) {
+#pragma unroll
+        for (int c = 0; c < RL; ++c) {
+          const cd v = scratch[((size_t)t * m + i) * RL + c];
+          acc[c].x += v.x;
+          acc[c].y += v.y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (act && s == 0) {
+#pragma unroll
+    for (int c = 0; c < RL; ++c) store(i, c, acc[c]);
+  }
+  __syncthreads();
+}
+
+// out[i + m*c] = sum_j Sinv[i + m*j] * W[j + m*c]  (Sinv in global/L2; K split like prod_a)
+template <int RL>
+__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, const cd* W, cd* out, cd* scratch,
+                                          size_t scratch_cap) {
+  const int tid = threadIdx.x;
+  int ks = 1;
+  while (ks < 8 && 2 * ks * m <= NT && (size_t)(2 * ks) * m * RL <= scratch_cap) ks *= 2;
+  const int i = tid % m, s = tid / m;
+  const bool act = s < ks;
+  cd acc[RL];
+#pragma unroll
+  for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+  if (act) {
+    const int jper = (m + ks - 1) / ks;
+    const int j1 = min(m, (s + 1) * jper);
+#pragma unroll 4
+    for (int j = s * jper; j < j1; ++j) {
+      const cd a = Sinv[i + (size_t)m * j];
+#pragma unroll
+      for (int c = 0; c < RL; ++c) cfma(acc[c], a, W[j + m * c]);
+    }
+  }
+  __syncthreads();
+  if (ks > 1) {
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < RL; ++c) scratch[((size_t)s * m + i) * RL + c] = acc[c];
+    }
+    __syncthreads();
+    if (act && s == 0) {
+      for (int t = 1; t < ks; ++t) {
+#pragma unroll
+        for (int c = 0; c < RL; ++c) {
+          const cd v = scratch[((size_t)t * m + i) * RL + c];
+          acc[c].x += v.x;
+          acc[c].y += v.y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (act && s == 0) {
+#pragma unroll
+    for (int c = 0; c < RL; ++c) out[i + m * c] = acc[c];
+  }
+  __syncthreads();
+}
+
+// ArgMinZ (inferLowRankV4.m:402-464) + N update (:319-320) + X/Z norms.  Contains exactly one
+// cluster sync.  On return nrm[0..3] hold THIS CTA's partial |X-Z|^2, |Z-Z0|^2, |X|^2, |Z|^2.
+template <int RL, int CS>
+__device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm, double mu, bool init_mode,
+                                     bool warm, double* nrm, int* sweeps_acc) {
+  const int tid = threadIdx.x;
+  const double imu = 1.0 / mu;
+  constexpr int NE = FN * RL;          // local elements
+  constexpr int NEC = NE / FTX;        // local E columns
+  // ---- N <- Z_in = X + N/mu
+  for (int idx = tid; idx < NE; idx += NT) {
+    cd v = sm.X[idx];
+    if (!init_mode) { const cd nn = sm.N[idx]; v.x = fma(nn.x, imu, v.x); v.y = fma(nn.y, imu, v.y); }
+    sm.N[idx] = v;
+  }
+  __syncthreads();
+  // ---- partial Gram over the local E columns (lower triangle)
+  const int gi = tid & 15, gj = tid >> 4;   // 256 threads = the 16 x 16 entries
+  {
+    cd acc = cmk(0.0, 0.0);
+    if (gi >= gj) {
+#pragma unroll 4
+      for (int e = 0; e < NEC; ++e) cfmabc(acc, sm.N[gi + FTX * e], sm.N[gj + FTX * e]);
+    }
+    sm.xG[gi + FTX * gj] = acc;
+  }
+  cl_sync<CS>();
+  if (gi >= gj) {
+    cd g = cmk(0.0, 0.0);
+#pragma unroll
+    for (int rk = 0; rk < CS; ++rk) {
+      const cd v = peer_ptr<cd, CS>(sm.xG, rk)[gi + FTX * gj];
+      g.x += v.x;
+      g.y += v.y;
+    }
+    if (gi == gj) g.y = 0.0;
+    sm.G[gi + FTX * gj] = g;
+    if (gi != gj) sm.G[gj + FTX * gi] = cmk(g.x, -g.y);
+  }
+  __syncthreads();
+  if (warm) {   // rotate into the previous eigenbasis: G <- U' G U (nearly diagonal), then refine U
+    cd t1 = cmk(0.0, 0.0);
+#pragma unroll 4
+    for (int k = 0; k < FTX; ++k) cfma(t1, sm.G[gi + FTX * k], sm.U[k + FTX * gj]);
+    sm.P[gi + FTX * gj] = t1;
+    __syncthreads();
+    cd t2 = cmk(0.0, 0.0);
+    if (gi >= gj) {
+#pragma unroll 4
+      for (int k = 0; k < FTX; ++k) cfmac(t2, sm.U[k + FTX * gi], sm.P[k + FTX * gj]);
+      if (gi == gj) t2.y = 0.0;
+    }
+    __syncthreads();
+    if (gi >= gj) {
+      sm.G[gi + FTX * gj] = t2;
+      if (gi != gj) sm.G[gj + FTX * gi] = cmk(t2.x, -t2.y);
+    }
+    __syncthreads();
+  }
+  const long long tj0 = clock64();
+  const int sw = jacobi16(sm.G, sm.P, sm.U, sm.pairs, sm.jprm, !warm);
+  if (tid == 0) sm.sc[20] += (double)(clock64() - tj0);
+  if (tid == 0) {
+    *sweeps_acc += sw;
+    int ord[FTX];
+    double s2[FTX], scl[FTX], ss[FTX];
+    for (int i = 0; i < FTX; ++i) { s2[i] = fmax(0.0, sm.G[i + FTX * i].x); ord[i] = i; scl[i] = 1.0; }
+    for (int i = 1; i < FTX; ++i) {   // stable descending insertion sort (:409)
+      int oi = ord[i]; double v = s2[oi]; int j = i - 1;
+      while (j >= 0 && s2[ord[j]] < v) { ord[j + 1] = ord[j]; --j; }
+      ord[j + 1] = oi;
+    }
+    for (int i = 0; i < FTX; ++i) ss[i] = s2[ord[i]];
+    int rl[4]; double fl[4];
+    const int ns = rank_profile_dev(FTX, FTX, m, FN, rank_one, rl, fl);
+    for (int k = 0; k < ns; ++k) {    // cascade :449-459
+      const int rr = rl[k]; const double f = fl[k];
+      double vr = 0.0, v = 0.0;
+      for (int i = 0; i < rr && i < FTX; ++i) vr += ss[i];
+      for (int i = 0; i < FTX; ++i) v += ss[i];
+      if (vr < v * f) {
+        const double scale = fmin(1.0, vr / (v - vr) * (1.0 / f - 1.0));
+        for (int i = rr; i < FTX; ++i) { ss[i] *= scale; scl[ord[i]] *= scale; }
+      }
+    }
+    int a = 0;
+    for (int i = 0; i < FTX; ++i) { if (scl[i] < 1.0) a = 1; sm.s2s[i] = sqrt(scl[i]); }
+    sm.ifl[0] = a;
+  }
+  __syncthreads();
+  const int any = sm.ifl[0];
+  if (any) {   // P = U diag(sqrt(s2_scale)) U'
+    cd acc = cmk(0.0, 0.0);
+#pragma unroll 4
+    for (int k = 0; k < FTX; ++k) {
+      const cd ui = sm.U[gi + FTX * k], uj = sm.U[gj + FTX * k];
+      const double s = sm.s2s[k];
+      cfmabc(acc, cmk(ui.x * s, ui.y * s), uj);
+    }
+    sm.P[gi + FTX * gj] = acc;
+  }
+  __syncthreads();
+  // ---- Z <- P Z_in (or Z_in), norms.  Item (e, ig): rows 4ig..4ig+3 of E column e; the owner of an
+  // element is the only thread touching Z there, so Z_old can be read and replaced in place.
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  constexpr int ITEMS = NEC * 4;
+  for (int it = tid; it < ITEMS; it += NT) {
+    const int ig = it & 3, e = it >> 2;
+    const cd* z = sm.N + FTX * e;
+    cd zn[4];
+    if (any) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) zn[u] = cmk(0.0, 0.0);
+#pragma unroll 4
+      for (int k = 0; k < FTX; ++k) {
+        const cd zz = z[k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cfma(zn[u], sm.P[(4 * ig + u) + FTX * k], zz);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) zn[u] = z[4 * ig + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = FTX * e + 4 * ig + u;
+      if (!init_mode) {
+        const cd zo = sm.Z[idx], x = sm.X[idx];
+        a0 += cabs2(cmk(x.x - zn[u].x, x.y - zn[u].y));
+        a1 += cabs2(cmk(zn[u].x - zo.x, zn[u].y - zo.y));
+        a2 += cabs2(x);
+        a3 += cabs2(zn[u]);
+      }
+      sm.Z[idx] = zn[u];
+    }
+  }
+  __syncthreads();
+  // ---- N <- mu (Z_in - Z)   (0 in init mode: N is not part of the :288 call)
+  for (int idx = tid; idx < NE; idx += NT) {
+    if (init_mode) {
+      sm.N[idx] = cmk(0.0, 0.0);
+    } else {
+      const cd zi = sm.N[idx], zn = sm.Z[idx];
+      sm.N[idx] = cmk(mu * (zi.x - zn.x), mu * (zi.y - zn.y));
+    }
+  }
+  if (!init_mode) {
+    double v[4] = {a0, a1, a2, a3};
+    block_sum<4>(v, sm.red);
+    nrm[0] = v[0]; nrm[1] = v[1]; nrm[2] = v[2]; nrm[3] = v[3];
+  } else {
+    __syncthreads();
+  }
+}
+
+template <int RL, int CS>
+__device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const FastDims& fd,
+                                const FastSmem<RL>& sm, cd* wsg, int rank) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = tk.m;
+  constexpr int r = RL * CS;
+  const int c0 = rank * RL;              // first global column owned by this CTA
+  const double cs = *tk.cscale;          // A_eff = cs * u
+  const double bsc = *tk.bscale;
+  const int rank_one = tk.rank_one_ptr ? *tk.rank_one_ptr : tk.rank_one;
+  cd* Sinv = wsg;
+  cd* AtY = wsg + (size_t)fd.maxm * fd.maxm;   // [256 x r], column c0+c owned by this CTA
+  const cd* lut = sm.lut;
+  const cd* lutc = sm.lut + 4;
+  cd* scratch = sm.WT;                   // WT | AX | G | P are contiguous (U must survive: warm start)
+  const size_t scratch_cap = 2 * (size_t)fd.maxm * RL + 2 * FTX * FTX;
+  cd* scratch2 = sm.G;                   // G | P (for the S^-1 product, which reads WT and writes AX)
+  const size_t scratch2_cap = 2 * FTX * FTX;
+
+  // ---- stage-local copies
+  if (tid < 4) {
+    const double re[4] = {1.0, 0.0, -1.0, 0.0}, im[4] = {0.0, 1.0, 0.0, -1.0};
+    sm.lut[tid] = cmk(re[tid], im[tid]);
+    sm.lut[4 + tid] = cmk(re[tid], -im[tid]);
+  }
+  for (int i = tid; i < m; i += NT) {
+    sm.rows_s[i] = tk.A.rows ? tk.A.rows[i] : i;
+    sm.Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
+  }
+  jacobi16_pairs(sm.pairs);
+  __syncthreads();
+  for (int idx = tid; idx < 16 * m; idx += NT) {
+    const int w = idx / m, i = idx - w * m;
+    sm.cik[w * m + i] = tk.codes[(size_t)sm.rows_s[i] * 16 + w];
+  }
+  __syncthreads();
+  {
+    const int k = tid;   // thread k packs code(i, k) for all i
+    for (int w = 0; w * 16 < m; ++w) {
+      uint32_t word = 0;
+      const int cnt = min(16, m - w * 16);
+      for (int j = 0; j < cnt; ++j) {
+        const uint32_t c = (sm.cik[(k >> 4) * m + (w * 16 + j)] >> (2 * (k & 15))) & 3u;
+        word |= c << (2 * j);
+      }
+      sm.cki[w * 256 + k] = word;
+    }
+  }
+  double nb2;
+  {
+    double v[1] = {0.0};
+    for (int i = tid; i < m; i += NT) v[0] += sm.Bs[i] * sm.Bs[i];
+    block_sum<1>(v, sm.red);
+    nb2 = v[0];
+  }
+  const double normB = sqrt(nb2);
+
+  // ---- S = I + A A' from exact phase counts (pairs split over the cluster), inverse by rank 0
+  {
+    const double cs2 = cs * cs;
+    for (int idx = tid + NT * rank; idx < m * m; idx += NT * CS) {
+      const int i = idx % m, j = idx / m;
+      if (i >= j) {
+        int re = 0, im = 0;
+        for (int w = 0; w < 16; ++w) {
+          uint32_t wi = sm.cik[w * m + i], wj = sm.cik[w * m + j];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const uint32_t d = (wi - wj) & 3u;     // u_i conj(u_j) = j^d
+            re += (d == 0u) - (d == 2u);
+            im += (d == 1u) - (d == 3u);
+            wi >>= 2;
+            wj >>= 2;
+          }
+        }
+        const cd v = cmk(((i == j) ? 1.0 : 0.0) + cs2 * re, (i == j) ? 0.0 : cs2 * im);
+        Sinv[i + (size_t)m * j] = v;
+        if (i != j) Sinv[j + (size_t)m * i] = cmk(v.x, -v.y);
+      }
+    }
+    __threadfence();
+    cl_sync<CS>();
+    if (rank == 0) spd_inverse(Sinv, m, scratch, scratch + m);
+    __threadfence();
+    cl_sync<CS>();
+  }
+
+  // ---- X = X0 (own columns), M = N = 0
+  for (int idx = tid; idx < FN * RL; idx += NT) {
+    sm.X[idx] = tk.X0[(size_t)FN * c0 + idx];
+    sm.N[idx] = cmk(0.0, 0.0);
+  }
+  for (int idx = tid; idx < m * RL; idx += NT) sm.M[idx] = cmk(0.0, 0.0);
+  __syncthreads();
+  // AX = A X  (:278)
+  prod_a<RL>(sm.cik, m, sm.X, lut, scratch, scratch_cap,
+             [&](int i, int c, cd v) { sm.AX[i + m * c] = cscale(v, cs); });
+  // rescale so |A X| matches |B|  (:279-286)
+  if (tk.sbr) {
+    double v[1] = {0.0};
+    for (int idx = tid; idx < m * RL; idx += NT) v[0] += cabs2(sm.AX[idx]);
+    block_sum<1>(v, sm.red);
+    if (tid == 0) sm.xsc[0] = v[0];
+    cl_sync<CS>();
+    double tot = 0.0;
+#pragma unroll
+    for (int rk = 0; rk < CS; ++rk) tot += peer_ptr<double, CS>(sm.xsc, rk)[0];
+    const double s = normB / sqrt(tot);
+    for (int idx = tid; idx < FN * RL; idx += NT) sm.X[idx] = cscale(sm.X[idx], s);
+    for (int idx = tid; idx < m * RL; idx += NT) sm.AX[idx] = cscale(sm.AX[idx], s);
+    cl_sync<CS>();   // peers are done with xsc[0] before it is reused
+  } else {
+    for (int c = warp; c < RL; c += NW) {
+      double a = 0.0;
+      for (int i = lane; i < m; i += 32) a += cabs2(sm.AX[i + m * c]);
+      a = warp_sum(a);
+      if (lane == 0) sm.colsc[c] = normB / sqrt(a);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < FN * RL; idx += NT) sm.X[idx] = cscale(sm.X[idx], sm.colsc[idx / FN]);
+    for (int idx = tid; idx < m * RL; idx += NT) sm.AX[idx] = cscale(sm.AX[idx], sm.colsc[idx / m]);
+  }
+  __syncthreads();
+  // Y = normalize_rows(AX, B)  (:287, :517-538)
+  if (tk.sbr) {
+    for (int i = tid; i < m; i += NT) {
+      double d2 = 0.0;
+      for (int c = 0; c < RL; ++c) d2 += cabs2(sm.AX[i + m * c]);
+      sm.xrow[i] = d2;
+    }
+    cl_sync<CS>();
+    const double isr = 1.0 / sqrt((double)r);
+    for (int i = tid; i < m; i += NT) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int rk = 0; rk < CS; ++rk) d2 += peer_ptr<double, CS>(sm.xrow, rk)[i];
+      double D = sqrt(d2);
+      const bool z = (D == 0.0);
+      if (z) D = 1.0;
+      const double f = sm.Bs[i] / D;
+      for (int c = 0; c < RL; ++c) {
+        const cd v = z ? cmk(isr, 0.0) : sm.AX[i + m * c];
+        sm.Y[i + m * c] = cscale(v, f);
+      }
+    }
+    cl_sync<CS>();
+  } else {
+    for (int idx = tid; idx < m * RL; idx += NT) {
+      const int i = idx % m;
+      cd v = sm.AX[idx];
+      double D = sqrt(cabs2(v));
+      if (D == 0.0) { v = cmk(1.0, 0.0); D = 1.0; }
+      sm.Y[idx] = cscale(v, sm.Bs[i] / D);
+    }
+  }
+  __syncthreads();
+  int sweeps = 0;
+  double nz[4];
+  fast_argmin_z<RL, CS>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);   // Z = ArgMinZ(X, 0, 1)  (:288)
+  __syncthreads();
+  if (prm.need_dual) {   // AtY = A' Y  (:289)
+    cd acc[RL];
+#pragma unroll
+    for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+    prod_ah<RL>(sm.cki, m, sm.Y, m, lutc, acc);
+#pragma unroll
+    for (int c = 0; c < RL; ++c) AtY[tid + (size_t)FN * (c0 + c)] = cscale(acc[c], cs);
+  }
+
+  double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
+  int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
+  const int rout = tk.sbr ? r : 1;
+  if (tid == 0) { sm.sc[20] = 0.0; sm.sc[21] = 0.0; sm.sc[22] = 0.0; sm.sc[23] = 0.0; }
+  const long long tl0 = clock64();
+
+  for (int it = 1; it <= prm.maxiter; ++it) {
+    const double imu = 1.0 / mu;
+    const long long tx0 = clock64();
+    double* xsc = sm.xsc + (it & 1) * XS_SCAL;
+    double* xcol = sm.xcol + (it & 1) * SMALL_DMAX;
+    // ---- T = Y - M/mu  -> WT
+    for (int idx = tid; idx < m * RL; idx += NT) {
+      const cd y = sm.Y[idx], mm = sm.M[idx];
+      sm.WT[idx] = cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
+    }
+    __syncthreads();
+    // ---- V = A'T + (Z - N/mu)  -> X   (:383, first half)
+    {
+      cd acc[RL];
+#pragma unroll
+      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+      prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
+#pragma unroll
+      for (int c = 0; c < RL; ++c) {
+        const int p = tid + FN * c;
+        const cd z = sm.Z[p], nn = sm.N[p];
+        sm.X[p] = cmk(fma(acc[c].x, cs, fma(-nn.x, imu, z.x)), fma(acc[c].y, cs, fma(-nn.y, imu, z.y)));
+      }
+    }
+    __syncthreads();
+    // ---- W = A V -> WT ; AX = S^-1 W ; X = V - A' AX   (Woodbury form of inv(A'A+I) V)
+    prod_a<RL>(sm.cik, m, sm.X, lut, scratch, scratch_cap,
+               [&](int i, int c, cd v) { sm.WT[i + m * c] = cscale(v, cs); });
+    prod_sinv<RL>(Sinv, m, sm.WT, sm.AX, scratch2, scratch2_cap);
+    {
+      cd acc[RL];
+#pragma unroll
+      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+      prod_ah<RL>(sm.cki, m, sm.AX, m, lutc, acc);
+#pragma unroll
+      for (int c = 0; c < RL; ++c) {
+        const int p = tid + FN * c;
+        const cd x = sm.X[p];
+        sm.X[p] = cmk(fma(-acc[c].x, cs, x.x), fma(-acc[c].y, cs, x.y));
+      }
+    }
+    __syncthreads();
+    const long long tx1 = clock64();
+    if (tid == 0) sm.sc[21] += (double)(tx1 - tx0);
+    // ---- Y update (:308), M update (:315-316), objective (:323-340); Y0 - Y kept in WT for A'(Y-Y0)
+    double pYd2 = 0.0, pJM2 = 0.0, pY2 = 0.0, pAX2 = 0.0, obj2 = 0.0, nAX2 = 0.0;
+    const double i1mu = 1.0 / (1.0 + mu);
+    if (tk.sbr) {
+      for (int i = tid; i < m; i += NT) {
+        double d2 = 0.0, a2 = 0.0;
+        for (int c = 0; c < RL; ++c) {
+          const cd ax = sm.AX[i + m * c], mm = sm.M[i + m * c];
+          d2 += cabs2(cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y)));
+          a2 += cabs2(ax);
+        }
+        sm.xrow[i] = d2;
+        sm.xrow[fd.maxm + i] = a2;
+      }
+      cl_sync<CS>();
+      for (int i = tid; i < m; i += NT) {
+        double d2 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int rk = 0; rk < CS; ++rk) {
+          const double* pr = peer_ptr<double, CS>(sm.xrow, rk);
+          d2 += pr[i];
+          a2 += pr[fd.maxm + i];
+        }
+        double D = sqrt(d2);
+        const bool z = (D == 0.0);
+        if (z) D = 1.0;
+        const double f = (sm.Bs[i] / D + mu) * i1mu;
+        const double isr = 1.0 / sqrt((double)r);
+        for (int c = 0; c < RL; ++c) {
+          const int p = i + m * c;
+          const cd ax = sm.AX[p], mm = sm.M[p], yo = sm.Y[p];
+          const cd cc = z ? cmk(isr, 0.0) : cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y));
+          const cd yn = cscale(cc, f);
+          const cd jm = cmk(ax.x - yn.x, ax.y - yn.y);
+          const cd dy = cmk(yn.x - yo.x, yn.y - yo.y);
+          sm.Y[p] = yn;
+          sm.M[p] = cmk(fma(mu, jm.x, mm.x), fma(mu, jm.y, mm.y));
+          sm.WT[p] = dy;
+          pYd2 += cabs2(dy);
+          pJM2 += cabs2(jm);
+          pY2 += cabs2(yn);
+        }
+        nAX2 += a2;                      // cluster totals: identical in every CTA
+        const double dd = sqrt(a2) - sm.Bs[i];
+        obj2 += dd * dd;
+      }
+    } else {
+      for (int c = warp; c < RL; c += NW) {
+        double oc = 0.0;
+        for (int i = lane; i < m; i += 32) {
+          const int p = i + m * c;
+          const cd ax = sm.AX[p], mm = sm.M[p], yo = sm.Y[p];
+          cd cc = cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y));
+          double D = sqrt(cabs2(cc));
+          if (D == 0.0) { cc = cmk(1.0, 0.0); D = 1.0; }
+          const double f = (sm.Bs[i] / D + mu) * i1mu;
+          const cd yn = cscale(cc, f);
+          const cd jm = cmk(ax.x - yn.x, ax.y - yn.y);
+          const cd dy = cmk(yn.x - yo.x, yn.y - yo.y);
+          sm.Y[p] = yn;
+          sm.M[p] = cmk(fma(mu, jm.x, mm.x), fma(mu, jm.y, mm.y));
+          sm.WT[p] = dy;
+          pYd2 += cabs2(dy);
+          pJM2 += cabs2(jm);
+          pY2 += cabs2(yn);
+          const double a2 = cabs2(ax);
+          pAX2 += a2;
+          const double dd = sqrt(a2) - sm.Bs[i];
+          oc += dd * dd;
+        }
+        oc = warp_sum(oc);
+        if (lane == 0) xcol[c0 + c] = sqrt(oc);
+      }
+    }
+    {
+      double v[6] = {pYd2, pJM2, pY2, pAX2, obj2, nAX2};
+      block_sum<6>(v, sm.red);
+      pYd2 = v[0]; pJM2 = v[1]; pY2 = v[2]; pAX2 = v[3]; obj2 = v[4]; nAX2 = v[5];
+    }
+    // ---- A'(Y - Y0) (:309): advances AtY in global memory; only feeds res_dual
+    double pAtYd2 = 0.0, pAtY2 = 0.0;
+    if (prm.need_dual) {
+      cd acc[RL];
+#pragma unroll
+      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+      prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
+      double v[2] = {0.0, 0.0};
+#pragma unroll
+      for (int c = 0; c < RL; ++c) {
+        const size_t p = tid + (size_t)FN * (c0 + c);
+        const cd d = cscale(acc[c], cs);
+        cd a = AtY[p];
+        a.x += d.x;
+        a.y += d.y;
+        AtY[p] = a;
+        v[0] += cabs2(d);
+        v[1] += cabs2(a);
+      }
+      block_sum<2>(v, sm.red);
+      pAtYd2 = v[0]; pAtY2 = v[1];
+    }
+    const long long tx2 = clock64();
+    if (tid == 0) sm.sc[22] += (double)(tx2 - tx1);
+    // ---- Z, N update (:312, :319-320)
+    // warm-started from the previous eigenvectors; a cold start every 64 iterations re-orthonormalises U
+    fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (it & 63) != 0, nz, &sweeps);
+    // ---- cluster-wide scalars
+    if (tid == 0) {
+      xsc[0] = pYd2; xsc[1] = pJM2; xsc[2] = pY2; xsc[3] = pAX2; xsc[4] = pAtYd2; xsc[5] = pAtY2;
+      xsc[6] = nz[0]; xsc[7] = nz[1]; xsc[8] = nz[2]; xsc[9] = nz[3];
+    }
+    cl_sync<CS>();
+    double tot[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) tot[q] = 0.0;
+#pragma unroll
+    for (int rk = 0; rk < CS; ++rk) {
+      const double* pr = peer_ptr<double, CS>(xsc, rk);
+#pragma unroll
+      for (int q = 0; q < 10; ++q) tot[q] += pr[q];
+    }
+    const double nYd2 = tot[0], nJM2 = tot[1], nY2 = tot[2];
+    if (!tk.sbr) nAX2 = tot[3];
+    const double nAtYd2 = tot[4], nAtY2 = tot[5], nJN2 = tot[6], nZd2 = tot[7], nX2 = tot[8], nZ2 = tot[9];
+
+    // ---- best solution so far (:323-340); NaN objectives never win (MATLAB min skips NaN)
+    double obj; int jbest = -1;
+    if (tk.sbr) {
+      obj = sqrt(obj2);
+    } else {
+      obj = NAN;
+      for (int c = 0; c < r; ++c) {
+        const double oc = peer_ptr<double, CS>(xcol, c / RL)[c];
+        if (oc == oc && (jbest < 0 || oc < obj)) { obj = oc; jbest = c; }
+      }
+    }
+    if (obj < opt_obj) {
+      opt_obj = obj; opt_iter = it; opt_col = jbest; have_opt = 1;
+      if (tk.sbr) {
+        if (tk.Xout) for (int idx = tid; idx < FN * RL; idx += NT) tk.Xout[(size_t)FN * c0 + idx] = sm.X[idx];
+        if (tk.Yout) for (int idx = tid; idx < m * RL; idx += NT) tk.Yout[(size_t)m * c0 + idx] = sm.Y[idx];
+      } else if (jbest / RL == rank) {
+        const int cl = jbest - c0;
+        if (tk.Xout) for (int k = tid; k < FN; k += NT) tk.Xout[k] = sm.X[k + FN * cl];
+        if (tk.Yout) for (int i = tid; i < m; i += NT) tk.Yout[i] = sm.Y[i + m * cl];
+      }
+    }
+    // ---- residuals and stopping rule (:343-354)
+    const double res_prim = sqrt(nJM2 + nJN2);
+    const double res_dual = mu * sqrt(nAtYd2 + nZd2);
+    res_comb = sqrt(nJM2 + nJN2 + nYd2 + nZd2);
+    iters = it;
+    if (prm.need_dual) {
+      const double mx1 = fmax(sqrt(nAX2), sqrt(nY2)), mx2 = fmax(sqrt(nX2), sqrt(nZ2));
+      const double th_prim = prm.tol_abs * sqrt((double)(m + FN) * r) + prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2);
+      const double th_dual = prm.tol_abs * sqrt((double)FN * r * 2.0) + prm.tol_rel * sqrt(nAtY2 + nZ2);
+      const double th_comb = prm.tol_abs * sqrt((double)(m + FN) * r * 2.0) +
+                             prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2 + nY2 + nZ2);
+      if ((res_prim < th_prim && res_dual < th_dual) || (res_comb < th_comb)) { converged = 1; break; }
+    }
+    if (res_comb > last_res * 0.9) { mu *= prm.rho; ++bumps; }   // :358-361
+    last_res = res_comb;
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- outputs: the best iterate is already in place; all-NaN objectives give NaN (H4)
+  if (!have_opt) {
+    if (tk.sbr) {
+      if (tk.Xout) for (int idx = tid; idx < FN * RL; idx += NT) tk.Xout[(size_t)FN * c0 + idx] = cmk(NAN, NAN);
+      if (tk.Yout) for (int idx = tid; idx < m * RL; idx += NT) tk.Yout[(size_t)m * c0 + idx] = cmk(NAN, NAN);
+    } else if (rank == 0) {
+      if (tk.Xout) for (int k = tid; k < FN; k += NT) tk.Xout[k] = cmk(NAN, NAN);
+      if (tk.Yout) for (int i = tid; i < m; i += NT) tk.Yout[i] = cmk(NAN, NAN);
+    }
+  }
+  (void)rout;
+  if (tk.state) {   // [X Z N (n x r) | Y M (m x r)], own columns
+    cd* st = tk.state;
+    const size_t nr = (size_t)FN * r, mr = (size_t)m * r;
+    for (int idx = tid; idx < FN * RL; idx += NT) {
+      const size_t g = (size_t)FN * c0 + idx;
+      st[g] = sm.X[idx]; st[nr + g] = sm.Z[idx]; st[2 * nr + g] = sm.N[idx];
+    }
+    for (int idx = tid; idx < m * RL; idx += NT) {
+      const size_t g = (size_t)m * c0 + idx;
+      st[3 * nr + g] = sm.Y[idx]; st[3 * nr + mr + g] = sm.M[idx];
+    }
+  }
+  if (tk.scal && tid == 0 && rank == 0) {
+    tk.scal[SC_MU] = mu; tk.scal[SC_OPT_OBJ] = opt_obj; tk.scal[SC_ITERS] = iters;
+    tk.scal[SC_OPT_ITER] = opt_iter; tk.scal[SC_OPT_COL] = opt_col; tk.scal[SC_BUMPS] = bumps;
+    tk.scal[SC_CONVERGED] = converged; tk.scal[SC_RES_COMB] = res_comb; tk.scal[SC_SWEEPS] = sweeps;
+    tk.scal[9] = sm.sc[20]; tk.scal[10] = sm.sc[21]; tk.scal[11] = (double)(clock64() - tl0);
+    (void)sm.sc[22];
+  }
+  cl_sync<CS>();   // no CTA leaves (or reuses its exchange buffers) while a peer may still read them
+}
+
+template <int RL, int CS>
+__global__ void __launch_bounds__(NT, (RL <= 5) ? 2 : 1)
+fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const FastSmem<RL> sm = fast_carve<RL>(smem_raw, fd);
+  int rank = 0;
+  if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
+  const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
+  cd* wsg = wsbase + (size_t)cid * fd.ws_stride;
+  for (int t = cid; t < ntasks; t += ncl) {
+    const StageTask tk = tasks[t];
+    if (tk.active != nullptr && *tk.active != tk.active_expect) continue;   // cluster-uniform
+    run_fast<RL, CS>(tk, prm, fd, sm, wsg, rank);
+  }
+}
+
+}  // namespace twoace

@@ -5,7 +5,7 @@
 // is taken on the device and recorded in the per-instance InstCtl words, so the host issues a
 // fixed launch sequence with no round trips.
 #pragma once
-#include "admm_stage.cuh"
+#include "fast_stage.cuh"
 
 namespace twoace {
 
@@ -24,6 +24,8 @@ struct InstCtl {
   int y_rows;          // rows of the returned Y (m, or m_train after a roll-back)
   int trial_r1_mask;   // bit t set when trial t used the rank-one profile
   double trial_quality[3];
+  double c_scale;      // quantised codebooks: A_eff = c_scale * u(code)
+  int quant;           // 1 when every entry of A is c * {1, j, -1, -j}
 };
 
 // ---- pre-processing ----------------------------------------------------------------------
@@ -33,6 +35,7 @@ struct PrepTask {
   const cd* cb;        // codebook mode: row-major codebook
   const int* cbrows;   // codebook mode: row ids [m]
   double row_scale;    // codebook mode: A = row_scale * cb[rows]
+  double code_mag;     // codebook mode: |cb entry| of the quantised codebook (c_scale = a_scale * code_mag)
   const double* B;     // [m]
   int m;
   InstCtl* ctl;
@@ -74,6 +77,8 @@ __global__ void __launch_bounds__(NT) prep_kernel(const PrepTask* __restrict__ t
       c.need_r1 = 0; c.use_rank_one = 0; c.best_trial = -1; c.rolled_back = 0; c.y_rows = m;
       c.trial_r1_mask = 0;
       c.trial_quality[0] = c.trial_quality[1] = c.trial_quality[2] = NAN;
+      c.c_scale = c.a_scale * tk.code_mag;
+      c.quant = 0;
       *tk.ctl = c;
     }
     __syncthreads();
@@ -426,6 +431,55 @@ __global__ void __launch_bounds__(NT) final_kernel(const FinalTask* __restrict__
       ctl->rolled_back = rollback ? 1 : 0;
       ctl->y_rows = yr;
       *tk.quality_out = q;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- 2-bit phase-code extraction -----------------------------------------------------------------
+// A row-major matrix whose entries are all c * {1, j, -1, -j} (one common magnitude c, residues below
+// 1e-15 c tolerated: the shipped .mat codebooks carry cos(pi/2) = 6e-17) is re-expressed as 2-bit codes,
+// 16 per 32-bit word, 16 words per row (n = 256).  One CTA per matrix.
+struct QuantTask {
+  const cd* A_rm;      // rows x 256 row-major
+  int rows;
+  uint32_t* codes;     // rows x 16 words
+  double* mag_out;     // c (may be nullptr)
+  int* flag_out;       // 1 = quantised
+  InstCtl* ctl;        // optional: sets ctl->quant and ctl->c_scale = a_scale * c
+};
+
+__global__ void __launch_bounds__(NT) quant_kernel(const QuantTask* __restrict__ tasks, int ntasks) {
+  __shared__ int s_bad;
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const QuantTask tk = tasks[t];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    const cd a0 = tk.A_rm[0];
+    const double c = fmax(fabs(a0.x), fabs(a0.y));
+    const double tol = 1e-15 * c;
+    int bad = (c > 0.0) ? 0 : 1;
+    for (size_t w = tid; w < (size_t)tk.rows * 16; w += NT) {
+      const cd* a = tk.A_rm + w * 16;
+      uint32_t word = 0;
+      for (int j = 0; j < 16; ++j) {
+        const cd v = a[j];
+        uint32_t code;
+        if (fabs(v.y) <= tol && fabs(fabs(v.x) - c) <= tol) code = (v.x > 0.0) ? 0u : 2u;
+        else if (fabs(v.x) <= tol && fabs(fabs(v.y) - c) <= tol) code = (v.y > 0.0) ? 1u : 3u;
+        else { code = 0u; bad = 1; }
+        word |= code << (2 * j);
+      }
+      tk.codes[w] = word;
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (tid == 0) {
+      const int ok = s_bad ? 0 : 1;
+      *tk.flag_out = ok;
+      if (tk.mag_out) *tk.mag_out = c;
+      if (tk.ctl) { tk.ctl->quant = ok; tk.ctl->c_scale = tk.ctl->a_scale * c; }
     }
     __syncthreads();
   }

@@ -35,6 +35,8 @@ struct StageTask {
   const int* rank_one_ptr;  // optional device override of rank_one (decided by an earlier kernel)
   const int* active;    // device flag (nullptr = always active); inactive tasks return immediately
   int active_expect;    // task runs iff *active == active_expect
+  const uint32_t* codes;  // 2-bit phase codes of A.base rows (16 words per row, n = 256) or nullptr
+  const double* cscale;   // device scalar: A_eff = (*cscale) * u(code)   (valid when codes != nullptr)
   double* scal;         // [STAGE_SCAL] per-task bookkeeping (may be nullptr)
   double2* state;       // optional dump of final [X Z N (n x r each) | Y M (m x r each)] (may be nullptr)
 };

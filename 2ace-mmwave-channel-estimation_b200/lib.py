@@ -21,6 +21,7 @@ EXPORTS = [
     "twoace_stream", "twoace_launch_count", "twoace_synchronize", "twoace_solve_batch",
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
+    "twoace_set_option", "twoace_fast_launch_count",
 ]
 
 
@@ -97,6 +98,10 @@ def load() -> C.CDLL:
     lib.twoace_timing_collect.restype = C.c_int
     lib.twoace_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.twoace_fp64_peak.restype = C.c_int
+    lib.twoace_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.twoace_set_option.restype = C.c_int
+    lib.twoace_fast_launch_count.argtypes = [vp]
+    lib.twoace_fast_launch_count.restype = C.c_int64
     _lib = lib
     return lib
 
@@ -150,6 +155,13 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.twoace_synchronize(self.h))
+
+    def set_option(self, key: str, value: int):
+        self.check(self.lib.twoace_set_option(self.h, key.encode(), int(value)))
+
+    @property
+    def fast_launch_count(self) -> int:
+        return int(self.lib.twoace_fast_launch_count(self.h))
 
     def set_timing(self, on: bool):
         self.check(self.lib.twoace_set_timing(self.h, int(bool(on))))

@@ -132,6 +132,13 @@ int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, co
 int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m,
                                const double* A, const double* B, int r, double* Xs);
 
+/* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
+ * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
+ * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass. */
+int twoace_set_option(twoace_ctx* ctx, const char* key, int value);
+/* InferADMM launches that took the shared-memory cluster kernel since context creation. */
+int64_t twoace_fast_launch_count(const twoace_ctx* ctx);
+
 /* Measurement hooks (bench.py).  With timing on, every InferADMM stage-kernel launch is bracketed by
  * CUDA events on the context's stream; twoace_timing_collect synchronises, returns the summed
  * duration (ms) and launch count since the last collect, and resets the accumulators. */

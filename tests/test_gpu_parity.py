@@ -59,14 +59,25 @@ def test_spectral_init_n_by_n_branch(codebook, gpu_ctx):
     assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-9
 
 
+@pytest.fixture(params=["general", "fast_cs2", "fast_cs4"])
+def kernel_path(request, gpu_ctx):
+    """Run a test on the general kernel and on the shared-memory cluster kernel (cluster size 2 and 4)."""
+    gpu_ctx.set_option("fast", 0 if request.param == "general" else 1)
+    gpu_ctx.set_option("fast_cs", 4 if request.param == "fast_cs4" else 2)
+    yield request.param
+    gpu_ctx.set_option("fast", 1)
+    gpu_ctx.set_option("fast_cs", 2)
+
+
 @pytest.mark.parametrize("sbr,r,r1,nuc", [(True, 20, False, False), (False, 20, False, False),
                                           (True, 1, True, False), (True, 20, True, False),
                                           (True, 20, False, True), (False, 7, False, False)])
 @pytest.mark.parametrize("iters", [1, 2, 10, 100])
-def test_stage_state_parity(codebook, gpu_ctx, sbr, r, r1, nuc, iters):
+def test_stage_state_parity(codebook, gpu_ctx, kernel_path, sbr, r, r1, nuc, iters):
     import twoace_b200 as tw
     from twoace_b200 import solvers as sv
     At, Bt = _stage_case(codebook, 64)
+    fast0 = gpu_ctx.fast_launch_count
     X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
     snap = {iters: None}
     tro = admm.StageTrace()
@@ -84,14 +95,16 @@ def test_stage_state_parity(codebook, gpu_ctx, sbr, r, r1, nuc, iters):
     assert np.linalg.norm(Sg[0]["M"] - s["M"]) < tol * max(1.0, np.linalg.norm(s["M"]))
     assert np.linalg.norm(Sg[0]["N"] - s["N"]) < tol * max(1.0, np.linalg.norm(s["N"]))
     assert rel(Xg[0], Xo) < tol and rel(Yg[0], Yo) < tol
-    assert abs(W[0][0] - s["mu"]) <= 1e-12 * s["mu"]
+    assert abs(W[0][0] - tro.mu) <= 1e-12 * tro.mu
     assert int(W[0][2]) == iters
     assert int(W[0][3]) == tro.opt_iter and int(W[0][4]) == tro.opt_col     # bit-exact bookkeeping
     assert int(W[0][5]) == tro.n_mu_bumps
+    eligible = kernel_path != "general" and not nuc and r in (1, 20)
+    assert (gpu_ctx.fast_launch_count - fast0 == 1) == eligible      # the intended kernel really ran
 
 
-@pytest.mark.parametrize("M", [36, 361])
-def test_stage_parity_other_shapes(codebook, gpu_ctx, M):
+@pytest.mark.parametrize("M", [36, 121, 225, 361])
+def test_stage_parity_other_shapes(codebook, gpu_ctx, kernel_path, M):
     """M=36: K-split small-m path; M=361: explicit-inverse (non-Woodbury) branch."""
     import twoace_b200 as tw
     from twoace_b200 import solvers as sv
@@ -107,7 +120,7 @@ def test_stage_parity_other_shapes(codebook, gpu_ctx, M):
         assert rel(Sg[0]["Y"], snap[iters]["Y"]) < 1e-9
 
 
-def test_convergence_test_mode_matches_iteration_count(codebook, gpu_ctx):
+def test_convergence_test_mode_matches_iteration_count(codebook, gpu_ctx, kernel_path):
     import twoace_b200 as tw
     from twoace_b200 import solvers as sv
     At, Bt = _stage_case(codebook, 64)
@@ -161,7 +174,7 @@ def _check_full(res, out, insts, frac=0.95, stage_exact=True):
 
 @pytest.mark.parametrize("variant_name", ["V4", "V4_MULTI", "NUCLEAR"])
 @pytest.mark.parametrize("M", [64, 225])
-def test_full_solve_parity_default_tolerances(codebook, gpu_ctx, variant_name, M):
+def test_full_solve_parity_default_tolerances(codebook, gpu_ctx, kernel_path, variant_name, M):
     """The reference's own operating mode (no caller passes more than 4 arguments)."""
     import twoace_b200 as tw
     from twoace_b200 import harness as hz
@@ -274,3 +287,22 @@ def test_error_reporting(codebook, gpu_ctx):
     # the context stays usable after an error
     r = sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [ins.train_idx[:1]], tw.Params.default(maxiter=5), gpu_ctx)
     assert r.X.shape == (1, 256)
+
+
+def test_general_complex_A_takes_general_kernel(gpu_ctx):
+    """A non-quantised sensing matrix (e.g. the 8-phase 'Random_Phase_State' alphabet or beams*AD,
+    SURVEY.md §7.2) must not be forced onto the 2-bit path."""
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    rng = np.random.default_rng(3)
+    A = np.exp(1j * np.pi / 8 * rng.integers(0, 16, (60, 256))) / 16
+    B = np.abs(A @ (rng.standard_normal(256) + 1j * rng.standard_normal(256)))
+    B /= np.linalg.norm(B)
+    X0 = (rng.standard_normal((256, 20)) + 1j * rng.standard_normal((256, 20))) / 16
+    f0 = gpu_ctx.fast_launch_count
+    p = tw.Params.default(maxiter=20, tol_rel=0.0, tol_abs=0.0)
+    Xg, Yg, Sg, W = sv.infer_admm_batch([A], [B], [X0], True, False, TX, RX, p, ctx=gpu_ctx)
+    assert gpu_ctx.fast_launch_count == f0
+    snap = {20: None}
+    admm.infer_admm(A, B, X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 0.0, 0.0, 20, None, None, admm.argmin_z, None, snap)
+    assert rel(Sg[0]["X"], snap[20]["X"]) < 1e-9

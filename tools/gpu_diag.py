@@ -9,6 +9,8 @@ from oracle import admm
 np.set_printoptions(linewidth=200, precision=4)
 cb = hz.load_codebook()
 ctx = tw.Context(0)
+if len(sys.argv) > 1: ctx.set_option("fast", int(sys.argv[1]))
+if len(sys.argv) > 2: ctx.set_option("fast_cs", int(sys.argv[2]))
 
 def rel(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
@@ -97,3 +99,4 @@ for nbt in (148, 592):
     res = sv.solve_batch(tw.V4, [i.A for i in big], [i.B for i in big], tx, rx, [i.train_idx[:1] for i in big], p, ctx)
     dt = time.time() - t0
     print(f"throughput probe: {nbt} V4 solves in {dt:.2f}s = {nbt/dt:.1f} solves/s; total iters/inst {res.info[:,15].mean():.0f}; launches {ctx.launch_count}")
+print("fast launches:", ctx.fast_launch_count, "of", ctx.launch_count)

@@ -200,43 +200,26 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
   return 0;
 }
 
-static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
-                        int tx, int rx, size_t& cursor) {
+static bool fast_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
+  return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && !t.nuclear && n == FN && tx == FTX &&
+         rx == FTX && t.m <= 256 && (t.r == 20 || t.r == 1);
+}
+
+static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
+                                int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
   StageDims dm;
   dm.n = n; dm.tx = tx; dm.rx = rx; dm.maxm = 1; dm.maxr = 1; dm.dmax = 1;
-  bool nuc = false, coded = true, same_r = true;
-  int minm = 1 << 30;
+  bool nuc = false;
   for (const StageTask& t : tasks) {
     dm.maxm = std::max(dm.maxm, t.m);
-    minm = std::min(minm, t.m);
     dm.maxr = std::max(dm.maxr, t.r);
     dm.dmax = std::max(dm.dmax, use_woodbury(t.m, n) ? t.m : n);
     nuc = nuc || t.nuclear;
-    coded = coded && t.codes != nullptr && t.cscale != nullptr;
-    same_r = same_r && t.r == tasks[0].r;
   }
   const StageTask* dt = nullptr;
   int rc = upload_tasks(ctx, tasks, cursor, &dt);
   if (rc) return rc;
-  // ---- shared-memory cluster kernel: 16x16, quantised A, r in {20, 1}, m <= 256, V4 ArgMinZ
-  if (ctx->opt_fast && coded && same_r && !nuc && n == FN && tx == FTX && rx == FTX && dm.maxm <= 256 &&
-      (dm.maxr == 20 || dm.maxr == 1)) {
-    FastDims fd;
-    fd.maxm = dm.maxm; fd.mw = (dm.maxm + 15) / 16; fd.r = dm.maxr; fd.ws_stride = 0;
-    bool launched = false;
-    if (dm.maxr == 1) {
-      rc = launch_fast_t<1, 1>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
-    } else {
-      for (int attempt = 0; attempt < 2 && !launched && rc == 0; ++attempt) {
-        const int cs = (attempt == 0) ? ctx->opt_fast_cs : (ctx->opt_fast_cs == 2 ? 4 : 2);
-        if (cs == 2) rc = launch_fast_t<10, 2>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
-        else rc = launch_fast_t<5, 4>(ctx, dt, (int)tasks.size(), prm, fd, &launched);
-      }
-    }
-    if (rc) return rc;
-    if (launched) return 0;
-  }
   dm.ds = nuc ? std::max(tx, dm.maxr) : tx;
   if (dm.ds > SMALL_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "tx (or r for the nuclear variant) > %d", SMALL_DMAX);
   dm.ws_stride = (stage_ws_elems(dm) + 15) / 16 * 16;
@@ -260,6 +243,48 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
   }
   ctx->launches++;
   return 0;
+}
+
+// One InferADMM launch.  Tasks that qualify for the shared-memory cluster kernel (16x16, quantised A,
+// r in {20,1}, m <= 256, V4 ArgMinZ) are split off, so the kernel an instance runs on never depends on
+// its batch mates.
+static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
+                        int tx, int rx, size_t& cursor) {
+  if (tasks.empty()) return 0;
+  // groups: r = 20 on cluster size 2, r = 20 on cluster size 4, r = 1; the cluster size of an r = 20 task
+  // is decided by ITS OWN m (does the RL = 10 layout fit in shared memory?), never by the batch
+  std::vector<StageTask> grp[3], gen;
+  auto fits2 = [](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
+                           return fast_smem_bytes<10>(f) <= (size_t)227 * 1024; };
+  auto fits4 = [](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
+                           return fast_smem_bytes<5>(f) <= (size_t)227 * 1024; };
+  for (const StageTask& t : tasks) {
+    if (!fast_eligible(ctx, t, n, tx, rx)) { gen.push_back(t); continue; }
+    if (t.r == 1) { grp[2].push_back(t); continue; }
+    const bool want2 = ctx->opt_fast_cs == 2;
+    if (want2 && fits2(t.m)) grp[0].push_back(t);
+    else if (fits4(t.m)) grp[1].push_back(t);
+    else if (fits2(t.m)) grp[0].push_back(t);
+    else gen.push_back(t);
+  }
+  for (int g = 0; g < 3; ++g) {
+    std::vector<StageTask>& ft = grp[g];
+    if (ft.empty()) continue;
+    FastDims fd;
+    fd.maxm = 1;
+    for (const StageTask& t : ft) fd.maxm = std::max(fd.maxm, t.m);
+    fd.mw = (fd.maxm + 15) / 16; fd.r = (g == 2) ? 1 : 20; fd.ws_stride = 0;
+    const StageTask* dt = nullptr;
+    int rc = upload_tasks(ctx, ft, cursor, &dt);
+    if (rc) return rc;
+    bool launched = false;
+    if (g == 2) rc = launch_fast_t<1, 1>(ctx, dt, (int)ft.size(), prm, fd, &launched);
+    else if (g == 0) rc = launch_fast_t<10, 2>(ctx, dt, (int)ft.size(), prm, fd, &launched);
+    else rc = launch_fast_t<5, 4>(ctx, dt, (int)ft.size(), prm, fd, &launched);
+    if (rc) return rc;
+    if (!launched) FAIL(TWOACE_E_CUDA, "cluster kernel launch configuration rejected (group %d, maxm %d)", g, fd.maxm);
+  }
+  return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
 }
 
 static int launch_spectral(twoace_ctx* ctx, const std::vector<SpecTask>& tasks, int n, size_t& cursor) {
@@ -455,9 +480,9 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   CK(cudaMemsetAsync(d_sw, 0, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), ctx->stream));
 
   // task buffer: generous upper bound for all task arrays of this chunk
-  const size_t task_bytes = (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + T * (sizeof(SpecTask) + 4 * sizeof(StageTask) +
-                            2 * sizeof(OrthoTask) + 2 * sizeof(QualTask)) + sizeof(StageTask) + sizeof(FinalTask)) +
-                            256 * (8 * T + 8);
+  const size_t task_bytes = (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + T * (sizeof(SpecTask) + 8 * sizeof(StageTask) +
+                            2 * sizeof(OrthoTask) + 2 * sizeof(QualTask)) + 2 * sizeof(StageTask) + sizeof(FinalTask)) +
+                            256 * (16 * T + 16);
   rc = ensure(ctx, ctx->taskbuf, task_bytes);
   if (rc) return rc;
   size_t cursor = 0;
@@ -831,7 +856,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
   cd* d_Arm = (cd*)(base + o_Arm);
   double* d_one = (double*)(base + o_one);
   InstCtl* d_ctl = (InstCtl*)(base + o_ctl);
-  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + sizeof(StageTask)) + 4096); if (rc) return rc;
+  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * (sizeof(PrepTask) + sizeof(QuantTask) + 2 * sizeof(StageTask)) + 8192); if (rc) return rc;
   size_t cursor = 0;
   set_ones_kernel<<<1, 32, 0, ctx->stream>>>(d_one, 1);
   CK(cudaGetLastError());

@@ -415,7 +415,9 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   const cd* lut = sm.lut;
   const cd* lutc = sm.lut + 4;
   cd* scratch = sm.WT;                   // WT | AX | G | P are contiguous (U must survive: warm start)
-  const size_t scratch_cap = 2 * (size_t)fd.maxm * RL + 2 * FTX * FTX;
+  // capacity is taken from this task's m (not the launch's maxm) so that the K split, hence the
+  // summation order, never depends on the batch mates
+  const size_t scratch_cap = 2 * (size_t)m * RL + 2 * FTX * FTX;
   cd* scratch2 = sm.G;                   // G | P (for the S^-1 product, which reads WT and writes AX)
   const size_t scratch2_cap = 2 * FTX * FTX;
 

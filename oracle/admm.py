@@ -68,6 +68,9 @@ class StageTrace:
     opt_col: int = -1
     n_mu_bumps: int = 0
     res_comb: list = field(default_factory=list)
+    # conditioning of the column orthonormalisation that produced this stage's start point
+    # (lambda_min / lambda_max of X'*X at inferLowRankV4.m:242; NaN when not applicable)
+    ortho_cond: float = float("nan")
 
 
 def _fro(x) -> float:
@@ -335,7 +338,9 @@ def infer_low_rank_impl(A, B, Xs, tx, rx, lam, r, mu0, rho, tol_rel, tol_abs, ma
     X, Y, _ = infer_admm(A, B, Xs, True, use_rank_one, tx, rx, lam, mu0, rho, tol_rel, tol_abs,
                          maxiter, U, D, argmin_z_fn, tA)
     G = X.conj().T @ X
-    _, Vx = np.linalg.eigh(0.5 * (G + G.conj().T))
+    wx, Vx = np.linalg.eigh(0.5 * (G + G.conj().T))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tB.ortho_cond = float(max(wx[0], 0.0) / wx[-1]) if wx[-1] > 0 else 0.0
     X = X @ Vx
     X, Y, conv = infer_admm(A, B, X, False, use_rank_one, tx, rx, lam, mu0, rho, tol_rel, tol_abs,
                             maxiter, U, D, argmin_z_fn, tB)

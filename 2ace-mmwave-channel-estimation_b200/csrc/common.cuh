@@ -229,65 +229,125 @@ __device__ __forceinline__ void jacobi16_pairs(unsigned char* pairs) {
   }
 }
 
-__device__ inline int jacobi16(cd* G, cd* H, cd* V, const unsigned char* pairs, double* prm, bool init_v,
-                               int max_sweeps = 30) {
-  const int tid = threadIdx.x;
-  const int which = tid >> 7, k = (tid >> 4) & 7, i = tid & 15;
-  const int leader = tid & 16;   // lane (within the warp) of the first thread of this half-warp
-  if (init_v) V[tid] = cmk((i == (tid >> 4)) ? 1.0 : 0.0, 0.0);
+// Rotation J = [[c, sg],[-conj(sg), c]] annihilating the (p,q) entry b of [[a, b],[conj b, cc]].
+// A dependent FP64 op costs ~23 cycles on B200 (FP32: 4), so the ANGLE is derived in FP32 (relative
+// accuracy ~1e-7: the rotation then leaves a residual of 1e-7 |b|, which costs no extra sweep because
+// Jacobi's quadratic convergence only beats a 1e-7 contraction in its very last sweep) and the pair
+// (c, sg) is renormalised in FP64 so that J is unitary to 1 ulp: n2 = c^2 + |sg|^2 = 1 + eps, |eps| ~ 1e-7,
+// 1/sqrt(n2) = 1 - eps/2 + 3 eps^2/8 (eps^3 ~ 1e-21).
+__device__ __forceinline__ void jacobi_rot_sg(double a, double cc, cd b, double floor2, double& c, cd& sg) {
+  const double ab2 = cabs2(b);
+  c = 1.0;
+  sg = cmk(0.0, 0.0);
+  if (!(ab2 > floor2) || !(ab2 > 1.0e-34 * fabs(a * cc)) || !(ab2 > 1e-300)) return;
+  // scale-free FP32 inputs: tau = (cc - a) / (2 |b|)
+  const double d = cc - a;
+  float tauf, bxf, byf;
+  if (ab2 < 1e-60 || ab2 > 1e60 || fabs(d) > 1e30) {   // out of float range: rescale in double first
+    const double rab = rsqrt(ab2);
+    tauf = (float)fmin(fmax(0.5 * d * rab, -1e18), 1e18);
+    bxf = (float)(b.x * rab);
+    byf = (float)(b.y * rab);
+  } else {
+    const float rabf = rsqrtf((float)ab2);
+    tauf = 0.5f * (float)d * rabf;
+    bxf = (float)b.x * rabf;
+    byf = (float)b.y * rabf;
+  }
+  const float x1f = fmaf(tauf, tauf, 1.0f);
+  const float wf = x1f * rsqrtf(x1f);
+  const float tf = copysignf(__fdividef(1.0f, fabsf(tauf) + wf), tauf);
+  const float cf = rsqrtf(fmaf(tf, tf, 1.0f));
+  const float sf = tf * cf;
+  const double c0 = (double)cf, sx = (double)(sf * bxf), sy = (double)(sf * byf);
+  const double eps = fma(c0, c0, fma(sx, sx, sy * sy)) - 1.0;
+  const double rn = fma(eps, fma(eps, 0.375, -0.5), 1.0);
+  c = c0 * rn;
+  sg = cmk(sx * rn, sy * rn);
+}
+
+// 16 x 16 two-sided Jacobi, one barrier per round, one thread per matrix element.
+// Round = 8 disjoint pairs (round-robin table).  Thread (i, j) produces element (i, j) of J' G J from the
+// read-only previous G (ping-pong between Ga and Gb):
+//   n_ij = ca (cb g_ij + bp g_i,pj) + ap (cb g_pi,j + bp g_pi,pj)
+// with pi / pj the partners of i / j in this round and (ca, ap) / (cb, bp) the entries of J' / J that mix
+// them.  The 8 rotations are derived by lanes 0-7 of every warp (FP32 angle, FP64 renormalisation) and
+// shuffled to the lanes that need them; threads 0-127 also rotate the columns of V in place.
+//   tab [15][16] bytes: pair index (bits 0-2) | is-larger-member flag (bit 3) | partner index (bits 4-7)
+//   pairs [15][8][2] bytes: (p, q), p < q
+// Result: eigenvalues on the diagonal of Ga, eigenvectors in V.  With init_v == false the caller supplies
+// V and Ga = V' G0 V (warm start).  Requires exactly NT = 256 threads.
+__device__ __forceinline__ void jacobi16_tables(unsigned char* pairs, unsigned char* tab) {
+  for (int idx = threadIdx.x; idx < 15 * 8; idx += NT) {
+    int p, q;
+    rr_pair(8, idx >> 3, idx & 7, p, q);
+    pairs[2 * idx] = (unsigned char)p;
+    pairs[2 * idx + 1] = (unsigned char)q;
+    const int rd = idx >> 3, k = idx & 7;
+    tab[16 * rd + p] = (unsigned char)(k | (q << 4));
+    tab[16 * rd + q] = (unsigned char)(k | 8 | (p << 4));
+  }
+}
+
+__device__ inline int jacobi16(cd* Ga, cd* Gb, cd* V, const unsigned char* pairs, const unsigned char* tab,
+                               bool init_v, int max_sweeps = 30) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = tid & 15, j = tid >> 4;
+  if (init_v) V[tid] = cmk((i == j) ? 1.0 : 0.0, 0.0);
   double g = 0.0;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) g = fmax(g, fabs(G[17 * q].x));
+  for (int q = 0; q < 16; ++q) g = fmax(g, fabs(Ga[17 * q].x));
   const double floor_abs = 1.0e-18 * g;
   const double floor2 = floor_abs * floor_abs;
   __syncthreads();
-  cd* Mx = which ? V : G;
-  cd* Mo = which ? V : H;
+  const int kp = lane & 7;          // rotation derived by this lane
+  const int kv = j & 7;             // V update (threads 0-127): pair kv, row i
+  cd* Gin = Ga;
+  cd* Gout = Gb;
   int sweeps = 0;
-  for (; sweeps < max_sweeps;) {
+  while (sweeps < max_sweeps) {
     double smax = 0.0;
     for (int rd = 0; rd < 15; ++rd) {
-      const int p = pairs[2 * (rd * 8 + k)], q = pairs[2 * (rd * 8 + k) + 1];
-      double c = 1.0, s = 0.0;
-      cd e = cmk(1.0, 0.0);
-      if (i == 0) {   // one thread per half-warp derives the rotation, the other 15 receive it
-        jacobi_rot(G[17 * p].x, G[17 * q].x, G[p + 16 * q], floor2, c, s, e);
-        smax = fmax(smax, fabs(s));
-      }
-      c = __shfl_sync(0xffffffffu, c, leader);
-      s = __shfl_sync(0xffffffffu, s, leader);
-      e.x = __shfl_sync(0xffffffffu, e.x, leader);
-      e.y = __shfl_sync(0xffffffffu, e.y, leader);
-      {
-        const cd gp = Mx[i + 16 * p], gq = Mx[i + 16 * q];
-        const cd eq = cmul(e, gq);
-        Mo[i + 16 * p] = cmk(c * gp.x - s * eq.x, c * gp.y - s * eq.y);
-        Mo[i + 16 * q] = cmk(s * gp.x + c * eq.x, s * gp.y + c * eq.y);
-      }
-      if (tid < 128 && i == 0) { prm[4 * k] = c; prm[4 * k + 1] = s; prm[4 * k + 2] = e.x; prm[4 * k + 3] = e.y; }
-      __syncthreads();
-      if (tid < 128) {   // row update H -> G, item (pair k, column j = i)
-        const double c2 = prm[4 * k], s2 = prm[4 * k + 1];
-        const cd ec = cmk(prm[4 * k + 2], -prm[4 * k + 3]);
-        const cd hp = H[p + 16 * i], hq = H[q + 16 * i];
-        const cd eq = cmul(ec, hq);
-        cd np_ = cmk(c2 * hp.x - s2 * eq.x, c2 * hp.y - s2 * eq.y);
-        cd nq_ = cmk(s2 * hp.x + c2 * eq.x, s2 * hp.y + c2 * eq.y);
-        if (s2 != 0.0) {
-          if (i == p) np_.y = 0.0;
-          if (i == q) nq_.y = 0.0;
-          if (i == q) np_ = cmk(0.0, 0.0);
-          if (i == p) nq_ = cmk(0.0, 0.0);
-        }
-        G[p + 16 * i] = np_;
-        G[q + 16 * i] = nq_;
+      const unsigned char* pr = pairs + 16 * rd;
+      const int ti = tab[16 * rd + i], tj = tab[16 * rd + j];
+      const int p = pr[2 * kp], q = pr[2 * kp + 1];
+      double c;
+      cd sg;
+      jacobi_rot_sg(Gin[17 * p].x, Gin[17 * q].x, Gin[p + 16 * q], floor2, c, sg);
+      smax = fmax(smax, cabs2(sg));
+      const int ka = ti & 7, kb = tj & 7, pi = ti >> 4, pj = tj >> 4;
+      const cd gij = Gin[i + 16 * j], gipj = Gin[i + 16 * pj], gpij = Gin[pi + 16 * j], gpipj = Gin[pi + 16 * pj];
+      const double ca = __shfl_sync(0xffffffffu, c, ka), cb = __shfl_sync(0xffffffffu, c, kb);
+      const cd sa = cmk(__shfl_sync(0xffffffffu, sg.x, ka), __shfl_sync(0xffffffffu, sg.y, ka));
+      const cd sb = cmk(__shfl_sync(0xffffffffu, sg.x, kb), __shfl_sync(0xffffffffu, sg.y, kb));
+      // J' row i: (ca, ap): p-member: new_p = c row_p - sg row_q ; q-member: new_q = conj(sg) row_p + c row_q
+      const cd ap = (ti & 8) ? cmk(sa.x, -sa.y) : cmk(-sa.x, -sa.y);
+      // J col j:  (cb, bp): p-member: new_p = c col_p - conj(sg) col_q ; q-member: new_q = sg col_p + c col_q
+      const cd bp = (tj & 8) ? sb : cmk(-sb.x, sb.y);
+      const cd t1 = cadd(cscale(gij, cb), cmul(bp, gipj));
+      const cd t2 = cadd(cscale(gpij, cb), cmul(bp, gpipj));
+      cd n = cadd(cscale(t1, ca), cmul(ap, t2));
+      if (i == j) n.y = 0.0;
+      Gout[i + 16 * j] = n;
+      if (tid < 128) {   // V columns of pair kv, row i
+        const int pv = pr[2 * kv], qv = pr[2 * kv + 1];
+        const double cv = __shfl_sync(0xffffffffu, c, kv);
+        const cd sv = cmk(__shfl_sync(0xffffffffu, sg.x, kv), __shfl_sync(0xffffffffu, sg.y, kv));
+        const cd vp = V[i + 16 * pv], vq = V[i + 16 * qv];
+        V[i + 16 * pv] = csub(cscale(vp, cv), cmulc(sv, vq));
+        V[i + 16 * qv] = cadd(cmul(sv, vp), cscale(vq, cv));
       }
       __syncthreads();
+      cd* t = Gin; Gin = Gout; Gout = t;
     }
     ++sweeps;
     // quadratic convergence: a sweep whose largest rotation had |sin| <= 1e-8 leaves off-diagonals at the
-    // 1e-16 level, so no verification sweep is needed
-    if (!__syncthreads_or(smax > 1.0e-8)) break;
+    // 1e-16 level, so no verification sweep is needed (smax holds |sin|^2)
+    if (!__syncthreads_or(smax > 1.0e-16)) break;
+  }
+  if (Gin != Ga) {   // odd number of rounds: result is in Gb
+    Ga[tid] = Gb[tid];
+    __syncthreads();
   }
   return sweeps;
 }

@@ -45,13 +45,13 @@ __host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
   b += 3 * (size_t)FN * RL * sizeof(cd);                    // X Z N
   b += 4 * (size_t)d.maxm * RL * sizeof(cd);                // Y M WT AX
   b += 4 * (size_t)FTX * FTX * sizeof(cd);                  // G U P xG
-  b += 8 * sizeof(cd) + 256 + 32 * sizeof(double);          // LUTs, Jacobi pair table + rotation params
+  b += 8 * sizeof(cd) + 512 + 32 * sizeof(double);          // LUTs, Jacobi tables + rotation params
   b += (size_t)(FTX / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
   b += (size_t)d.maxm * sizeof(double) * 5;                 // Bs, xrow[2], rowtot[2]
   b += (2 * XS_SCAL + 2 * SMALL_DMAX) * sizeof(double);     // xsc (double-buffered), xcol (double-buffered)
-  b += (16 * NW + FTX + SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
+  b += (16 * NW + FTX + 2 * SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
   b += (size_t)d.mw * 256 * 4 + (size_t)16 * d.maxm * 4;    // cki, cik
-  b += (size_t)d.maxm * sizeof(int) + 16 * sizeof(int);
+  b += (size_t)d.maxm * sizeof(int) + 48 * sizeof(int);
   return b + 256;
 }
 
@@ -89,7 +89,7 @@ __device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
   s.P = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
   s.U = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);    // persistent across iterations (warm start)
   s.xG = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
-  s.pairs = (unsigned char*)p; p += 256;
+  s.pairs = (unsigned char*)p; p += 512;   // pair table [240] + element table [240]
   s.jprm = (double*)p; p += 32 * sizeof(double);
   s.lut = (cd*)p; p += 8 * sizeof(cd);
   const int h = FTX / 2 + 2;
@@ -103,12 +103,12 @@ __device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
   s.xcol = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
   s.red = (double*)p; p += 16 * NW * sizeof(double);
   s.s2s = (double*)p; p += FTX * sizeof(double);
-  s.colsc = (double*)p; p += SMALL_DMAX * sizeof(double);
+  s.colsc = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
   s.sc = (double*)p; p += 32 * sizeof(double);
   s.cki = (uint32_t*)p; p += (size_t)d.mw * 256 * 4;
   s.cik = (uint32_t*)p; p += (size_t)16 * d.maxm * 4;
   s.rows_s = (int*)p; p += (size_t)d.maxm * sizeof(int);
-  s.ifl = (int*)p; p += 16 * sizeof(int);
+  s.ifl = (int*)p; p += 48 * sizeof(int);
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;
   return s;
@@ -265,9 +265,17 @@ __device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm
   const int gi = tid & 15, gj = tid >> 4;   // 256 threads = the 16 x 16 entries
   {
     cd acc = cmk(0.0, 0.0);
-    if (gi >= gj) {
-#pragma unroll 4
-      for (int e = 0; e < NEC; ++e) cfmabc(acc, sm.N[gi + FTX * e], sm.N[gj + FTX * e]);
+    if (gi >= gj) {   // 4 independent accumulators: a dependent DFMA costs ~23 cycles
+      cd a0 = cmk(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+      static_assert(NEC % 4 == 0, "NEC must be a multiple of 4");
+#pragma unroll 2
+      for (int e = 0; e < NEC; e += 4) {
+        cfmabc(a0, sm.N[gi + FTX * e], sm.N[gj + FTX * e]);
+        cfmabc(a1, sm.N[gi + FTX * (e + 1)], sm.N[gj + FTX * (e + 1)]);
+        cfmabc(a2, sm.N[gi + FTX * (e + 2)], sm.N[gj + FTX * (e + 2)]);
+        cfmabc(a3, sm.N[gi + FTX * (e + 3)], sm.N[gj + FTX * (e + 3)]);
+      }
+      acc = cmk((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
     }
     sm.xG[gi + FTX * gj] = acc;
   }
@@ -286,15 +294,27 @@ __device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm
   }
   __syncthreads();
   if (warm) {   // rotate into the previous eigenbasis: G <- U' G U (nearly diagonal), then refine U
-    cd t1 = cmk(0.0, 0.0);
-#pragma unroll 4
-    for (int k = 0; k < FTX; ++k) cfma(t1, sm.G[gi + FTX * k], sm.U[k + FTX * gj]);
-    sm.P[gi + FTX * gj] = t1;
+    cd t1 = cmk(0.0, 0.0), t1b = t1, t1c = t1, t1d = t1;
+#pragma unroll
+    for (int k = 0; k < FTX; k += 4) {
+      cfma(t1, sm.G[gi + FTX * k], sm.U[k + FTX * gj]);
+      cfma(t1b, sm.G[gi + FTX * (k + 1)], sm.U[(k + 1) + FTX * gj]);
+      cfma(t1c, sm.G[gi + FTX * (k + 2)], sm.U[(k + 2) + FTX * gj]);
+      cfma(t1d, sm.G[gi + FTX * (k + 3)], sm.U[(k + 3) + FTX * gj]);
+    }
+    sm.P[gi + FTX * gj] = cmk((t1.x + t1b.x) + (t1c.x + t1d.x), (t1.y + t1b.y) + (t1c.y + t1d.y));
     __syncthreads();
     cd t2 = cmk(0.0, 0.0);
     if (gi >= gj) {
-#pragma unroll 4
-      for (int k = 0; k < FTX; ++k) cfmac(t2, sm.U[k + FTX * gi], sm.P[k + FTX * gj]);
+      cd t2b = t2, t2c = t2, t2d = t2;
+#pragma unroll
+      for (int k = 0; k < FTX; k += 4) {
+        cfmac(t2, sm.U[k + FTX * gi], sm.P[k + FTX * gj]);
+        cfmac(t2b, sm.U[(k + 1) + FTX * gi], sm.P[(k + 1) + FTX * gj]);
+        cfmac(t2c, sm.U[(k + 2) + FTX * gi], sm.P[(k + 2) + FTX * gj]);
+        cfmac(t2d, sm.U[(k + 3) + FTX * gi], sm.P[(k + 3) + FTX * gj]);
+      }
+      t2 = cmk((t2.x + t2b.x) + (t2c.x + t2d.x), (t2.y + t2b.y) + (t2c.y + t2d.y));
       if (gi == gj) t2.y = 0.0;
     }
     __syncthreads();
@@ -304,49 +324,102 @@ __device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm
     }
     __syncthreads();
   }
+  // ---- cheap exact screen (warm only): by Schur-Horn the r largest diagonal entries of U'GU sum to at most
+  // the r largest eigenvalues, while the trace is the same.  If every constraint C(r_k, f_k) of :449-459
+  // already holds for the sorted DIAGONAL (with a 1e-12 margin) it holds for the spectrum, no stage fires,
+  // s2_scale == 1 everywhere and :461 leaves Z = Z_in: the eigen-decomposition is not needed at all.
+  bool need_eig = true;
+  if (warm) {
+    if (tid < FTX) sm.colsc[tid] = fmax(0.0, sm.G[tid + FTX * tid].x);
+    __syncthreads();
+    if (tid < FTX) {
+      const double v = sm.colsc[tid];
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < FTX; ++j) { const double o = sm.colsc[j]; rank += (o > v) || (o == v && j < tid); }
+      sm.colsc[FTX + rank] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double pre[FTX + 1];
+      pre[0] = 0.0;
+#pragma unroll
+      for (int i = 0; i < FTX; ++i) pre[i + 1] = pre[i] + sm.colsc[FTX + i];
+      int rl[4]; double fl[4];
+      const int ns = rank_profile_dev(FTX, FTX, m, FN, rank_one, rl, fl);
+      int ok = 1;
+      for (int k = 0; k < ns; ++k) ok &= (pre[min(rl[k], FTX)] >= pre[FTX] * fl[k] * (1.0 + 1e-12)) ? 1 : 0;
+      sm.ifl[1] = ok;
+    }
+    __syncthreads();
+    need_eig = sm.ifl[1] == 0;
+  }
+  int any = 0;
+  if (need_eig) {
   const long long tj0 = clock64();
-  const int sw = jacobi16(sm.G, sm.P, sm.U, sm.pairs, sm.jprm, !warm);
+  const int sw = jacobi16(sm.G, sm.P, sm.U, sm.pairs, sm.pairs + 256, !warm);
   if (tid == 0) sm.sc[20] += (double)(clock64() - tj0);
-  if (tid == 0) {
-    *sweeps_acc += sw;
-    int ord[FTX];
-    double s2[FTX], scl[FTX], ss[FTX];
-    for (int i = 0; i < FTX; ++i) { s2[i] = fmax(0.0, sm.G[i + FTX * i].x); ord[i] = i; scl[i] = 1.0; }
-    for (int i = 1; i < FTX; ++i) {   // stable descending insertion sort (:409)
-      int oi = ord[i]; double v = s2[oi]; int j = i - 1;
-      while (j >= 0 && s2[ord[j]] < v) { ord[j + 1] = ord[j]; --j; }
-      ord[j + 1] = oi;
-    }
-    for (int i = 0; i < FTX; ++i) ss[i] = s2[ord[i]];
-    int rl[4]; double fl[4];
-    const int ns = rank_profile_dev(FTX, FTX, m, FN, rank_one, rl, fl);
-    for (int k = 0; k < ns; ++k) {    // cascade :449-459
-      const int rr = rl[k]; const double f = fl[k];
-      double vr = 0.0, v = 0.0;
-      for (int i = 0; i < rr && i < FTX; ++i) vr += ss[i];
-      for (int i = 0; i < FTX; ++i) v += ss[i];
-      if (vr < v * f) {
-        const double scale = fmin(1.0, vr / (v - vr) * (1.0 / f - 1.0));
-        for (int i = rr; i < FTX; ++i) { ss[i] *= scale; scl[ord[i]] *= scale; }
-      }
-    }
-    int a = 0;
-    for (int i = 0; i < FTX; ++i) { if (scl[i] < 1.0) a = 1; sm.s2s[i] = sqrt(scl[i]); }
-    sm.ifl[0] = a;
+  // eigenvalues clamped (:408) and ranked in descending order, stable (:409): one thread per eigenvalue
+  if (tid < FTX) sm.colsc[tid] = fmax(0.0, sm.G[tid + FTX * tid].x);
+  __syncthreads();
+  if (tid < FTX) {
+    const double v = sm.colsc[tid];
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < FTX; ++j) { const double o = sm.colsc[j]; rank += (o > v) || (o == v && j < tid); }
+    sm.colsc[FTX + rank] = v;          // sorted values
+    sm.ifl[16 + tid] = rank;           // position of eigenvalue tid in the sorted order
   }
   __syncthreads();
-  const int any = sm.ifl[0];
+  if (tid == 0) {
+    *sweeps_acc += sw;
+    // prefix sums of the sorted spectrum (tree-ish: 4 chains) then the cascade of :449-459 in O(1) per
+    // stage: with cf = product of the scales applied so far (to every index >= r_prev),
+    //   head_k = head_{k-1} + cf (pre[r_k] - pre[r_{k-1}]),  v = head_k + cf (pre[16] - pre[r_k])
+    double pre[FTX + 1];
+    pre[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < FTX; ++i) pre[i + 1] = pre[i] + sm.colsc[FTX + i];
+    int rl[4]; double fl[4];
+    const int ns = rank_profile_dev(FTX, FTX, m, FN, rank_one, rl, fl);
+    double cf = 1.0, head = 0.0;
+    int rprev = 0;
+    double cfs[4];
+    for (int k = 0; k < ns; ++k) {
+      const int rr = min(rl[k], FTX);
+      head += cf * (pre[rr] - pre[rprev]);
+      const double v = head + cf * (pre[FTX] - pre[rr]);
+      if (head < v * fl[k]) cf *= fmin(1.0, head / (v - head) * (1.0 / fl[k] - 1.0));
+      cfs[k] = cf;
+      rprev = rr;
+    }
+    // s2_scale of sorted position pos: product of the scales of the stages with r_k <= pos
+    for (int pos = 0; pos < FTX; ++pos) {
+      double sc = 1.0;
+      for (int k = 0; k < ns; ++k) if (pos >= rl[k]) sc = cfs[k];
+      sm.colsc[2 * FTX + pos] = sc;
+    }
+    sm.ifl[0] = (cf < 1.0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid < FTX) sm.s2s[tid] = sqrt(sm.colsc[2 * FTX + sm.ifl[16 + tid]]);
+  __syncthreads();
+  any = sm.ifl[0];
   if (any) {   // P = U diag(sqrt(s2_scale)) U'
-    cd acc = cmk(0.0, 0.0);
-#pragma unroll 4
+    cd ac[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ac[u] = cmk(0.0, 0.0);
+#pragma unroll
     for (int k = 0; k < FTX; ++k) {
       const cd ui = sm.U[gi + FTX * k], uj = sm.U[gj + FTX * k];
       const double s = sm.s2s[k];
-      cfmabc(acc, cmk(ui.x * s, ui.y * s), uj);
+      cfmabc(ac[k & 3], cmk(ui.x * s, ui.y * s), uj);
     }
-    sm.P[gi + FTX * gj] = acc;
+    sm.P[gi + FTX * gj] = cmk((ac[0].x + ac[1].x) + (ac[2].x + ac[3].x), (ac[0].y + ac[1].y) + (ac[2].y + ac[3].y));
   }
   __syncthreads();
+  if (tid == 0) sm.ifl[2] += 1;   // eigen-decompositions actually performed
+  }   // need_eig
   // ---- Z <- P Z_in (or Z_in), norms.  Item (e, ig): rows 4ig..4ig+3 of E column e; the owner of an
   // element is the only thread touching Z there, so Z_old can be read and replaced in place.
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -431,7 +504,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     sm.rows_s[i] = tk.A.rows ? tk.A.rows[i] : i;
     sm.Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
   }
-  jacobi16_pairs(sm.pairs);
+  jacobi16_tables(sm.pairs, sm.pairs + 256);
   __syncthreads();
   for (int idx = tid; idx < 16 * m; idx += NT) {
     const int w = idx / m, i = idx - w * m;
@@ -560,6 +633,8 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   __syncthreads();
   int sweeps = 0;
   double nz[4];
+  if (tid == 0) sm.ifl[2] = 0;
+  __syncthreads();
   fast_argmin_z<RL, CS>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);   // Z = ArgMinZ(X, 0, 1)  (:288)
   __syncthreads();
   if (prm.need_dual) {   // AtY = A' Y  (:289)
@@ -575,6 +650,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
   const int rout = tk.sbr ? r : 1;
   if (tid == 0) { sm.sc[20] = 0.0; sm.sc[21] = 0.0; sm.sc[22] = 0.0; sm.sc[23] = 0.0; }
+  // sm.ifl[2] counts eigen-decompositions since the stage began (set to 0 before the :288 call)
   const long long tl0 = clock64();
 
   for (int it = 1; it <= prm.maxiter; ++it) {
@@ -726,7 +802,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     if (tid == 0) sm.sc[22] += (double)(tx2 - tx1);
     // ---- Z, N update (:312, :319-320)
     // warm-started from the previous eigenvectors; a cold start every 64 iterations re-orthonormalises U
-    fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (it & 63) != 0, nz, &sweeps);
+    fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (sm.ifl[2] & 63) != 0, nz, &sweeps);
     // ---- cluster-wide scalars
     if (tid == 0) {
       xsc[0] = pYd2; xsc[1] = pJM2; xsc[2] = pY2; xsc[3] = pAX2; xsc[4] = pAtYd2; xsc[5] = pAtY2;

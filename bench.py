@@ -219,6 +219,10 @@ def ours_arm(args, wl, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = tw.Context(local_rank)
+    if args.fast_cs:
+        ctx.set_option("fast_cs", args.fast_cs)
+    if args.no_fast:
+        ctx.set_option("fast", 0)
     variant = getattr(tw, wl["variant"])
     T = 3 if wl["variant"] == "V4_MULTI" else 1
     tpc = args.trials_per_cell
@@ -364,6 +368,8 @@ def main():
     ap.add_argument("--workload", default="config1", choices=sorted(WORKLOADS))
     ap.add_argument("--trials-per-cell", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-cs", type=int, default=None, help="cluster size of the r=20 stages (2 or 4)")
+    ap.add_argument("--no-fast", action="store_true", help="force the general kernel")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.trials_per_cell is None:

@@ -201,8 +201,8 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
 }
 
 static bool fast_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
-  return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && !t.nuclear && n == FN && tx == FTX &&
-         rx == FTX && t.m <= 256 && (t.r == 20 || t.r == 1);
+  return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
+         t.m <= 256 && (t.r == 20 || t.r == 1) && (!t.nuclear || t.r == 1 || t.m >= 26);
 }
 
 static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
@@ -254,10 +254,14 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
   // groups: r = 20 on cluster size 2, r = 20 on cluster size 4, r = 1; the cluster size of an r = 20 task
   // is decided by ITS OWN m (does the RL = 10 layout fit in shared memory?), never by the batch
   std::vector<StageTask> grp[3], gen;
-  auto fits2 = [](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
-                           return fast_smem_bytes<10>(f) <= (size_t)227 * 1024; };
-  auto fits4 = [](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
-                           return fast_smem_bytes<5>(f) <= (size_t)227 * 1024; };
+  bool nuc = false;
+  for (const StageTask& t : tasks) nuc = nuc || t.nuclear;     // a launch is all-nuclear or all-V4
+  auto fits2 = [nuc](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
+                              f.nuclear = nuc; f.ds = nuc ? 20 : 16;
+                              return fast_smem_bytes<10>(f) <= (size_t)227 * 1024; };
+  auto fits4 = [nuc](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
+                              f.nuclear = nuc; f.ds = nuc ? 20 : 16;
+                              return fast_smem_bytes<5>(f) <= (size_t)227 * 1024; };
   for (const StageTask& t : tasks) {
     if (!fast_eligible(ctx, t, n, tx, rx)) { gen.push_back(t); continue; }
     if (t.r == 1) { grp[2].push_back(t); continue; }
@@ -274,6 +278,7 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     fd.maxm = 1;
     for (const StageTask& t : ft) fd.maxm = std::max(fd.maxm, t.m);
     fd.mw = (fd.maxm + 15) / 16; fd.r = (g == 2) ? 1 : 20; fd.ws_stride = 0;
+    fd.nuclear = nuc ? 1 : 0; fd.ds = (nuc && g != 2) ? 20 : 16;
     const StageTask* dt = nullptr;
     int rc = upload_tasks(ctx, ft, cursor, &dt);
     if (rc) return rc;
@@ -847,7 +852,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
   Bump bp;
   const size_t o_Arm = bp.take(a_off[nb] * sizeof(cd)), o_one = bp.take(sizeof(double));
   const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
-  const bool try_codes = ctx->opt_fast && n == FN && tx == FTX && rx == FTX && !nuclear && (r == 20 || r == 1);
+  const bool try_codes = ctx->opt_fast && n == FN && tx == FTX && rx == FTX && (r == 20 || r == 1);
   const size_t o_codes = try_codes ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
   const size_t o_qflag = try_codes ? bp.take((size_t)nb * sizeof(int)) : 0;
   const size_t o_mag = try_codes ? bp.take((size_t)nb * sizeof(double)) : 0;

@@ -235,25 +235,18 @@ __device__ __forceinline__ void jacobi16_pairs(unsigned char* pairs) {
 // Jacobi's quadratic convergence only beats a 1e-7 contraction in its very last sweep) and the pair
 // (c, sg) is renormalised in FP64 so that J is unitary to 1 ulp: n2 = c^2 + |sg|^2 = 1 + eps, |eps| ~ 1e-7,
 // 1/sqrt(n2) = 1 - eps/2 + 3 eps^2/8 (eps^3 ~ 1e-21).
-__device__ __forceinline__ void jacobi_rot_sg(double a, double cc, cd b, double floor2, double& c, cd& sg) {
+__device__ __forceinline__ void jacobi_rot_sg(double a, double cc, cd b, double floor2, double inv_g, double& c,
+                                              cd& sg) {
   const double ab2 = cabs2(b);
   c = 1.0;
   sg = cmk(0.0, 0.0);
   if (!(ab2 > floor2) || !(ab2 > 1.0e-34 * fabs(a * cc)) || !(ab2 > 1e-300)) return;
-  // scale-free FP32 inputs: tau = (cc - a) / (2 |b|)
-  const double d = cc - a;
-  float tauf, bxf, byf;
-  if (ab2 < 1e-60 || ab2 > 1e60 || fabs(d) > 1e30) {   // out of float range: rescale in double first
-    const double rab = rsqrt(ab2);
-    tauf = (float)fmin(fmax(0.5 * d * rab, -1e18), 1e18);
-    bxf = (float)(b.x * rab);
-    byf = (float)(b.y * rab);
-  } else {
-    const float rabf = rsqrtf((float)ab2);
-    tauf = 0.5f * (float)d * rabf;
-    bxf = (float)b.x * rabf;
-    byf = (float)b.y * rabf;
-  }
+  // FP32 angle on inputs normalised by g = max|diag| (inv_g = 1/g): |b|^2/g^2 lies in (1e-36, ~1] and
+  // |cc - a|/g <= 2, safely inside the float range; tau = (cc - a) / (2 |b|)
+  const float bxn = (float)(b.x * inv_g), byn = (float)(b.y * inv_g), dn = (float)((cc - a) * inv_g);
+  const float rabf = rsqrtf(fmaxf(fmaf(bxn, bxn, byn * byn), 1e-37f));
+  const float tauf = fminf(fmaxf(0.5f * dn * rabf, -1e18f), 1e18f);
+  const float bxf = bxn * rabf, byf = byn * rabf;
   const float x1f = fmaf(tauf, tauf, 1.0f);
   const float wf = x1f * rsqrtf(x1f);
   const float tf = copysignf(__fdividef(1.0f, fabsf(tauf) + wf), tauf);
@@ -266,76 +259,112 @@ __device__ __forceinline__ void jacobi_rot_sg(double a, double cc, cd b, double 
   sg = cmk(sx * rn, sy * rn);
 }
 
-// 16 x 16 two-sided Jacobi, one barrier per round, one thread per matrix element.
-// Round = 8 disjoint pairs (round-robin table).  Thread (i, j) produces element (i, j) of J' G J from the
-// read-only previous G (ping-pong between Ga and Gb):
+// D x D two-sided Jacobi (D even, D <= 20), one barrier per round, one thread per matrix element (two when
+// D*D > NT).  Round = D/2 disjoint pairs (round-robin table).  Thread (i, j) produces element (i, j) of
+// J' G J from the read-only previous G (ping-pong between Ga and Gb):
 //   n_ij = ca (cb g_ij + bp g_i,pj) + ap (cb g_pi,j + bp g_pi,pj)
 // with pi / pj the partners of i / j in this round and (ca, ap) / (cb, bp) the entries of J' / J that mix
-// them.  The 8 rotations are derived by lanes 0-7 of every warp (FP32 angle, FP64 renormalisation) and
-// shuffled to the lanes that need them; threads 0-127 also rotate the columns of V in place.
-//   tab [15][16] bytes: pair index (bits 0-2) | is-larger-member flag (bit 3) | partner index (bits 4-7)
-//   pairs [15][8][2] bytes: (p, q), p < q
+// them.  The D/2 rotations are derived by the first lanes of every warp (FP32 angle, FP64 renormalisation)
+// and shuffled to the lanes that need them; the first D*D/2 threads also rotate the columns of V in place.
+//   tab   [D-1][D]      bytes: pair index (bits 0-3) | is-larger-member flag (bit 7) ; partner in tab2
+//   tab2  [D-1][D]      bytes: partner index
+//   pairs [D-1][D/2][2] bytes: (p, q), p < q
 // Result: eigenvalues on the diagonal of Ga, eigenvectors in V.  With init_v == false the caller supplies
 // V and Ga = V' G0 V (warm start).  Requires exactly NT = 256 threads.
-__device__ __forceinline__ void jacobi16_tables(unsigned char* pairs, unsigned char* tab) {
-  for (int idx = threadIdx.x; idx < 15 * 8; idx += NT) {
+template <int D>
+struct JacobiTab {
+  static constexpr int ROUNDS = D - 1, HALF = D / 2;
+  static constexpr int PAIRS_BYTES = ROUNDS * HALF * 2, TAB_BYTES = ROUNDS * D;
+  static constexpr int BYTES = (PAIRS_BYTES + 2 * TAB_BYTES + 15) / 16 * 16;
+};
+
+template <int D>
+__device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
+  unsigned char* pairs = mem;
+  unsigned char* tab = mem + JacobiTab<D>::PAIRS_BYTES;
+  unsigned char* tab2 = tab + JacobiTab<D>::TAB_BYTES;
+  constexpr int H = D / 2;
+  for (int idx = threadIdx.x; idx < (D - 1) * H; idx += NT) {
+    const int rd = idx / H, k = idx - rd * H;
     int p, q;
-    rr_pair(8, idx >> 3, idx & 7, p, q);
+    rr_pair(H, rd, k, p, q);
     pairs[2 * idx] = (unsigned char)p;
     pairs[2 * idx + 1] = (unsigned char)q;
-    const int rd = idx >> 3, k = idx & 7;
-    tab[16 * rd + p] = (unsigned char)(k | (q << 4));
-    tab[16 * rd + q] = (unsigned char)(k | 8 | (p << 4));
+    tab[D * rd + p] = (unsigned char)k;
+    tab[D * rd + q] = (unsigned char)(k | 128);
+    tab2[D * rd + p] = (unsigned char)q;
+    tab2[D * rd + q] = (unsigned char)p;
   }
 }
 
-__device__ inline int jacobi16(cd* Ga, cd* Gb, cd* V, const unsigned char* pairs, const unsigned char* tab,
-                               bool init_v, int max_sweeps = 30) {
+template <int D>
+__device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
+                                   int max_sweeps = 30) {
+  static_assert(D % 2 == 0 && D <= 20 && D * D <= 2 * NT, "unsupported dimension");
+  constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
+  const unsigned char* pairs = mem;
+  const unsigned char* tab = mem + JacobiTab<D>::PAIRS_BYTES;
+  const unsigned char* tab2 = tab + JacobiTab<D>::TAB_BYTES;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int i = tid & 15, j = tid >> 4;
-  if (init_v) V[tid] = cmk((i == j) ? 1.0 : 0.0, 0.0);
+  if (init_v) {
+    for (int e = tid; e < E; e += NT) V[e] = cmk((e % D == e / D) ? 1.0 : 0.0, 0.0);
+  }
   double g = 0.0;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) g = fmax(g, fabs(Ga[17 * q].x));
+  for (int q = 0; q < D; ++q) g = fmax(g, fabs(Ga[(D + 1) * q].x));
   const double floor_abs = 1.0e-18 * g;
   const double floor2 = floor_abs * floor_abs;
+  const double inv_g = (g > 0.0) ? 1.0 / g : 0.0;
   __syncthreads();
-  const int kp = lane & 7;          // rotation derived by this lane
-  const int kv = j & 7;             // V update (threads 0-127): pair kv, row i
+  const int kp = lane % H;          // rotation derived by this lane
   cd* Gin = Ga;
   cd* Gout = Gb;
   int sweeps = 0;
   while (sweeps < max_sweeps) {
     double smax = 0.0;
-    for (int rd = 0; rd < 15; ++rd) {
-      const unsigned char* pr = pairs + 16 * rd;
-      const int ti = tab[16 * rd + i], tj = tab[16 * rd + j];
+    for (int rd = 0; rd < D - 1; ++rd) {
+      const unsigned char* pr = pairs + 2 * H * rd;
       const int p = pr[2 * kp], q = pr[2 * kp + 1];
       double c;
       cd sg;
-      jacobi_rot_sg(Gin[17 * p].x, Gin[17 * q].x, Gin[p + 16 * q], floor2, c, sg);
+      jacobi_rot_sg(Gin[(D + 1) * p].x, Gin[(D + 1) * q].x, Gin[p + D * q], floor2, inv_g, c, sg);
       smax = fmax(smax, cabs2(sg));
-      const int ka = ti & 7, kb = tj & 7, pi = ti >> 4, pj = tj >> 4;
-      const cd gij = Gin[i + 16 * j], gipj = Gin[i + 16 * pj], gpij = Gin[pi + 16 * j], gpipj = Gin[pi + 16 * pj];
-      const double ca = __shfl_sync(0xffffffffu, c, ka), cb = __shfl_sync(0xffffffffu, c, kb);
-      const cd sa = cmk(__shfl_sync(0xffffffffu, sg.x, ka), __shfl_sync(0xffffffffu, sg.y, ka));
-      const cd sb = cmk(__shfl_sync(0xffffffffu, sg.x, kb), __shfl_sync(0xffffffffu, sg.y, kb));
-      // J' row i: (ca, ap): p-member: new_p = c row_p - sg row_q ; q-member: new_q = conj(sg) row_p + c row_q
-      const cd ap = (ti & 8) ? cmk(sa.x, -sa.y) : cmk(-sa.x, -sa.y);
-      // J col j:  (cb, bp): p-member: new_p = c col_p - conj(sg) col_q ; q-member: new_q = sg col_p + c col_q
-      const cd bp = (tj & 8) ? sb : cmk(-sb.x, sb.y);
-      const cd t1 = cadd(cscale(gij, cb), cmul(bp, gipj));
-      const cd t2 = cadd(cscale(gpij, cb), cmul(bp, gpipj));
-      cd n = cadd(cscale(t1, ca), cmul(ap, t2));
-      if (i == j) n.y = 0.0;
-      Gout[i + 16 * j] = n;
-      if (tid < 128) {   // V columns of pair kv, row i
-        const int pv = pr[2 * kv], qv = pr[2 * kv + 1];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = tid + u * NT;
+        const bool on = e < E;
+        const int i = on ? e % D : 0, j = on ? e / D : 0;
+        const int ti = tab[D * rd + i], tj = tab[D * rd + j];
+        const int pi = tab2[D * rd + i], pj = tab2[D * rd + j];
+        const int ka = ti & 127, kb = tj & 127;
+        const double ca = __shfl_sync(0xffffffffu, c, ka), cb = __shfl_sync(0xffffffffu, c, kb);
+        const cd sa = cmk(__shfl_sync(0xffffffffu, sg.x, ka), __shfl_sync(0xffffffffu, sg.y, ka));
+        const cd sb = cmk(__shfl_sync(0xffffffffu, sg.x, kb), __shfl_sync(0xffffffffu, sg.y, kb));
+        if (on) {
+          const cd gij = Gin[i + D * j], gipj = Gin[i + D * pj], gpij = Gin[pi + D * j], gpipj = Gin[pi + D * pj];
+          // J' row i: (ca, ap): p-member: new_p = c row_p - sg row_q ; q-member: new_q = conj(sg) row_p + c row_q
+          const cd ap = (ti & 128) ? cmk(sa.x, -sa.y) : cmk(-sa.x, -sa.y);
+          // J col j:  (cb, bp): p-member: new_p = c col_p - conj(sg) col_q ; q-member: new_q = sg col_p + c col_q
+          const cd bp = (tj & 128) ? sb : cmk(-sb.x, sb.y);
+          const cd t1 = cadd(cscale(gij, cb), cmul(bp, gipj));
+          const cd t2 = cadd(cscale(gpij, cb), cmul(bp, gpipj));
+          cd n = cadd(cscale(t1, ca), cmul(ap, t2));
+          if (i == j) n.y = 0.0;
+          Gout[e] = n;
+        }
+      }
+      // V columns: item (pair kv, row iv), H*D items
+      for (int it = tid; it < ((H * D + 31) / 32) * 32; it += NT) {
+        const bool on = it < H * D;
+        const int kv = on ? it / D : 0, iv = on ? it % D : 0;
         const double cv = __shfl_sync(0xffffffffu, c, kv);
         const cd sv = cmk(__shfl_sync(0xffffffffu, sg.x, kv), __shfl_sync(0xffffffffu, sg.y, kv));
-        const cd vp = V[i + 16 * pv], vq = V[i + 16 * qv];
-        V[i + 16 * pv] = csub(cscale(vp, cv), cmulc(sv, vq));
-        V[i + 16 * qv] = cadd(cmul(sv, vp), cscale(vq, cv));
+        if (on) {
+          const int pv = pr[2 * kv], qv = pr[2 * kv + 1];
+          const cd vp = V[iv + D * pv], vq = V[iv + D * qv];
+          V[iv + D * pv] = csub(cscale(vp, cv), cmulc(sv, vq));
+          V[iv + D * qv] = cadd(cmul(sv, vp), cscale(vq, cv));
+        }
       }
       __syncthreads();
       cd* t = Gin; Gin = Gout; Gout = t;
@@ -346,7 +375,7 @@ __device__ inline int jacobi16(cd* Ga, cd* Gb, cd* V, const unsigned char* pairs
     if (!__syncthreads_or(smax > 1.0e-16)) break;
   }
   if (Gin != Ga) {   // odd number of rounds: result is in Gb
-    Ga[tid] = Gb[tid];
+    for (int e = tid; e < E; e += NT) Ga[e] = Gb[e];
     __syncthreads();
   }
   return sweeps;

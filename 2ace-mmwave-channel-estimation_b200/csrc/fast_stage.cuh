@@ -32,6 +32,8 @@ struct FastDims {
   int maxm;          // largest m in the launch
   int mw;            // ceil(maxm/16): words per k of the [i-word][k] code copy
   int r;             // total columns (CS * RL)
+  int ds;            // shared eig dimension: 16 (V4: tx x tx) or max(16, r) (nuclear: r x r)
+  int nuclear;
   size_t ws_stride;  // global workspace elements (cd) per cluster
 };
 
@@ -44,12 +46,12 @@ __host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
   size_t b = 0;
   b += 3 * (size_t)FN * RL * sizeof(cd);                    // X Z N
   b += 4 * (size_t)d.maxm * RL * sizeof(cd);                // Y M WT AX
-  b += 4 * (size_t)FTX * FTX * sizeof(cd);                  // G U P xG
-  b += 8 * sizeof(cd) + 512 + 32 * sizeof(double);          // LUTs, Jacobi tables + rotation params
-  b += (size_t)(FTX / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
+  b += 4 * (size_t)d.ds * d.ds * sizeof(cd);                // G P U xG
+  b += 8 * sizeof(cd) + 1280 + 32 * sizeof(double);         // LUTs, Jacobi tables + rotation params
+  b += (size_t)(d.ds / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
   b += (size_t)d.maxm * sizeof(double) * 5;                 // Bs, xrow[2], rowtot[2]
   b += (2 * XS_SCAL + 2 * SMALL_DMAX) * sizeof(double);     // xsc (double-buffered), xcol (double-buffered)
-  b += (16 * NW + FTX + 2 * SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
+  b += (16 * NW + 3 * SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
   b += (size_t)d.mw * 256 * 4 + (size_t)16 * d.maxm * 4;    // cki, cik
   b += (size_t)d.maxm * sizeof(int) + 48 * sizeof(int);
   return b + 256;
@@ -85,14 +87,14 @@ __device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
   s.M = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
   s.WT = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
   s.AX = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
-  s.G = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
-  s.P = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
-  s.U = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);    // persistent across iterations (warm start)
-  s.xG = (cd*)p; p += (size_t)FTX * FTX * sizeof(cd);
-  s.pairs = (unsigned char*)p; p += 512;   // pair table [240] + element table [240]
+  s.G = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
+  s.P = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
+  s.U = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);    // persistent across iterations (warm start)
+  s.xG = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
+  s.pairs = (unsigned char*)p; p += 1280;   // Jacobi pair / element tables (D = 16 or 20)
   s.jprm = (double*)p; p += 32 * sizeof(double);
   s.lut = (cd*)p; p += 8 * sizeof(cd);
-  const int h = FTX / 2 + 2;
+  const int h = d.ds / 2 + 2;
   s.js.e = (cd*)p; p += (size_t)h * sizeof(cd);
   s.js.cs = (double*)p; p += (size_t)h * sizeof(double);
   s.js.sn = (double*)p; p += (size_t)h * sizeof(double);
@@ -102,7 +104,7 @@ __device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
   s.xsc = (double*)p; p += 2 * XS_SCAL * sizeof(double);
   s.xcol = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
   s.red = (double*)p; p += 16 * NW * sizeof(double);
-  s.s2s = (double*)p; p += FTX * sizeof(double);
+  s.s2s = (double*)p; p += SMALL_DMAX * sizeof(double);
   s.colsc = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
   s.sc = (double*)p; p += 32 * sizeof(double);
   s.cki = (uint32_t*)p; p += (size_t)d.mw * 256 * 4;
@@ -126,118 +128,130 @@ __device__ __forceinline__ T* peer_ptr(T* p, int rank) {
   else return p;
 }
 
-// acc[c] += sum_i conj(u(i,k)) * Op[i + ldo*c]   for this thread's k (A' product, one thread per k)
+// A' product, register-tiled 2 (k) x RL (columns) with the reduction over i split over a lane pair:
+//   thread t: s = t & 1, k0 = t >> 1, k1 = k0 + 128, rows i = s, s + 2, s + 4, ...
+// Every operand Op[i, c] loaded from shared memory feeds 8 DFMAs (a broadcast LDS.128 costs 4 cycles of the
+// shared-memory pipe per warp, so one load per 4 DFMAs made the products shared-memory bound).  After the
+// pair reduction lane s keeps the result for k = k0 + 128 s, returned in acc[]; kout = that k.
 template <int RL>
-__device__ __forceinline__ void prod_ah(const uint32_t* cki, int m, const cd* Op, int ldo, const cd* lutc,
-                                        cd (&acc)[RL]) {
-  const int k = threadIdx.x;
-  for (int w = 0; w * 16 < m; ++w) {
-    uint32_t word = cki[w * 256 + k];
-    const int cnt = min(16, m - w * 16);
-    const cd* op = Op + w * 16;
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      const cd a = lutc[word & 3u];
-      word >>= 2;
+__device__ __forceinline__ int prod_ah(const uint32_t* cki, int m, const cd* Op, int ldo, const cd* lutc,
+                                       cd (&acc)[RL]) {
+  const int tid = threadIdx.x;
+  const int s = tid & 1, k0 = tid >> 1, k1 = k0 + 128;
+  cd a0[RL], a1[RL];
 #pragma unroll
-      for (int c = 0; c < RL; ++c) cfma(acc[c], a, op[j + ldo * c]);
+  for (int c = 0; c < RL; ++c) { a0[c] = cmk(0.0, 0.0); a1[c] = cmk(0.0, 0.0); }
+  for (int w = 0; w * 16 < m; ++w) {
+    uint32_t w0 = cki[w * 256 + k0] >> (2 * s), w1 = cki[w * 256 + k1] >> (2 * s);
+    const int cnt = (min(16, m - w * 16) - s + 1) >> 1;   // rows 16w + s, 16w + s + 2, ... below m
+    const cd* op = Op + w * 16 + s;
+#pragma unroll 2
+    for (int q = 0; q < cnt; ++q) {
+      const cd u0 = lutc[w0 & 3u], u1 = lutc[w1 & 3u];
+      w0 >>= 4;
+      w1 >>= 4;
+#pragma unroll
+      for (int c = 0; c < RL; ++c) {
+        const cd t = op[2 * q + ldo * c];
+        cfma(a0[c], u0, t);
+        cfma(a1[c], u1, t);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < RL; ++c) {
+    // lane s keeps k = k0 + 128 s: it needs its own partial of that k plus the partner's
+    const cd mine = s ? a1[c] : a0[c];
+    const cd give = s ? a0[c] : a1[c];
+    acc[c].x += mine.x + __shfl_xor_sync(0xffffffffu, give.x, 1);
+    acc[c].y += mine.y + __shfl_xor_sync(0xffffffffu, give.y, 1);
+  }
+  return k0 + 128 * s;
+}
+
+// largest power of two ks <= 16 with ks * m <= NT: the reduction index is split over ks ADJACENT lanes
+// (interleaved: lane s takes indices congruent to s mod ks, so shared-memory reads of consecutive lanes hit
+// consecutive 16-byte words) and the partial sums are combined with warp shuffles.  ks depends on m only,
+// so the summation order of an instance never depends on its batch mates.
+__device__ __forceinline__ int ksplit_for(int m, int kmax) {
+  int ks = 1;
+  while (ks < kmax && 2 * ks * m <= NT) ks *= 2;
+  return ks;
+}
+
+template <int RL>
+__device__ __forceinline__ void group_reduce(cd (&acc)[RL], int ks) {
+  for (int o = 1; o < ks; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < RL; ++c) {
+      acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, o);
+      acc[c].y += __shfl_xor_sync(0xffffffffu, acc[c].y, o);
     }
   }
 }
 
-// store(i, c, sum_k u(i,k) * V[k + 256*c]); the k range is split over thread groups when m is small
+// store(i, c, sum_k u(i,k) * V[k + 256*c])   (A product), register-tiled 2 (rows i) x RL (columns):
+// thread (row pair ip, lane-group member s) handles rows 2 ip, 2 ip + 1 and k = s, s + ks, ...
 template <int RL, class StoreF>
-__device__ __forceinline__ void prod_a(const uint32_t* cik, int m, const cd* V, const cd* lut, cd* scratch,
-                                       size_t scratch_cap, StoreF store) {
+__device__ __forceinline__ void prod_a(const uint32_t* cik, int m, const cd* V, const cd* lut, StoreF store) {
   const int tid = threadIdx.x;
-  int ks = 1;
-  while (ks < 16 && 2 * ks * m <= NT && (size_t)(2 * ks) * m * RL <= scratch_cap) ks *= 2;
-  const int i = tid % m, s = tid / m;
-  const bool act = s < ks;
-  cd acc[RL];
+  const int mp = (m + 1) >> 1;               // row pairs
+  const int ks = ksplit_for(mp, 16);
+  const int ip = tid / ks, s = tid - ip * ks;
+  const bool act = ip < mp;
+  const int i0 = 2 * ip, i1 = min(2 * ip + 1, m - 1);
+  cd a0[RL], a1[RL];
 #pragma unroll
-  for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+  for (int c = 0; c < RL; ++c) { a0[c] = cmk(0.0, 0.0); a1[c] = cmk(0.0, 0.0); }
   if (act) {
-    const int wper = 16 / ks;
-    for (int w = s * wper; w < (s + 1) * wper; ++w) {
-      uint32_t word = cik[w * m + i];
-      const cd* v = V + w * 16;
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const cd a = lut[word & 3u];
-        word >>= 2;
-#pragma unroll
-        for (int c = 0; c < RL; ++c) cfma(acc[c], a, v[j + FN * c]);
-      }
-    }
-  }
-  __syncthreads();   // scratch may alias buffers other threads were still reading
-  if (ks > 1) {
-    if (act) {
-#pragma unroll
-      for (int c = 0; c < RL; ++c) scratch[((size_t)s * m + i) * RL + c] = acc[c];
-    }
-    __syncthreads();
-    if (act && s == 0) {
-      for (int t = 1; t < ks; ++t) {
+    const int per = 16 / ks;   // codes of each word handled by this lane
+    for (int w = 0; w < 16; ++w) {
+      const uint32_t w0 = cik[w * m + i0] >> (2 * s), w1 = cik[w * m + i1] >> (2 * s);
+      const cd* v = V + w * 16 + s;
+#pragma unroll 2
+      for (int t = 0; t < per; ++t) {
+        const cd u0 = lut[(w0 >> (2 * ks * t)) & 3u], u1 = lut[(w1 >> (2 * ks * t)) & 3u];
 #pragma unroll
         for (int c = 0; c < RL; ++c) {
-          const cd v = scratch[((size_t)t * m + i) * RL + c];
-          acc[c].x += v.x;
-          acc[c].y += v.y;
+          const cd x = v[ks * t + FN * c];
+          cfma(a0[c], u0, x);
+          cfma(a1[c], u1, x);
         }
       }
     }
-    __syncthreads();
   }
+  group_reduce<RL>(a0, ks);
+  group_reduce<RL>(a1, ks);
   if (act && s == 0) {
 #pragma unroll
-    for (int c = 0; c < RL; ++c) store(i, c, acc[c]);
+    for (int c = 0; c < RL; ++c) store(i0, c, a0[c]);
+    if (2 * ip + 1 < m) {
+#pragma unroll
+      for (int c = 0; c < RL; ++c) store(i1, c, a1[c]);
+    }
   }
   __syncthreads();
 }
 
-// out[i + m*c] = sum_j Sinv[i + m*j] * W[j + m*c]  (Sinv in global/L2; K split like prod_a)
+// out[i + m*c] = sum_j Sinv[i + m*j] * W[j + m*c]  (Sinv in global/L2)
 template <int RL>
-__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, const cd* W, cd* out, cd* scratch,
-                                          size_t scratch_cap) {
+__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, const cd* W, cd* out) {
   const int tid = threadIdx.x;
-  int ks = 1;
-  while (ks < 8 && 2 * ks * m <= NT && (size_t)(2 * ks) * m * RL <= scratch_cap) ks *= 2;
-  const int i = tid % m, s = tid / m;
-  const bool act = s < ks;
+  const int ks = ksplit_for(m, 8);
+  const int i = tid / ks, s = tid - i * ks;
+  const bool act = i < m;
   cd acc[RL];
 #pragma unroll
   for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
   if (act) {
-    const int jper = (m + ks - 1) / ks;
-    const int j1 = min(m, (s + 1) * jper);
 #pragma unroll 4
-    for (int j = s * jper; j < j1; ++j) {
+    for (int j = s; j < m; j += ks) {
       const cd a = Sinv[i + (size_t)m * j];
 #pragma unroll
       for (int c = 0; c < RL; ++c) cfma(acc[c], a, W[j + m * c]);
     }
   }
-  __syncthreads();
-  if (ks > 1) {
-    if (act) {
-#pragma unroll
-      for (int c = 0; c < RL; ++c) scratch[((size_t)s * m + i) * RL + c] = acc[c];
-    }
-    __syncthreads();
-    if (act && s == 0) {
-      for (int t = 1; t < ks; ++t) {
-#pragma unroll
-        for (int c = 0; c < RL; ++c) {
-          const cd v = scratch[((size_t)t * m + i) * RL + c];
-          acc[c].x += v.x;
-          acc[c].y += v.y;
-        }
-      }
-    }
-    __syncthreads();
-  }
+  group_reduce<RL>(acc, ks);
   if (act && s == 0) {
 #pragma unroll
     for (int c = 0; c < RL; ++c) out[i + m * c] = acc[c];
@@ -357,7 +371,7 @@ __device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm
   int any = 0;
   if (need_eig) {
   const long long tj0 = clock64();
-  const int sw = jacobi16(sm.G, sm.P, sm.U, sm.pairs, sm.pairs + 256, !warm);
+  const int sw = jacobi_small<FTX>(sm.G, sm.P, sm.U, sm.pairs, !warm);
   if (tid == 0) sm.sc[20] += (double)(clock64() - tj0);
   // eigenvalues clamped (:408) and ranked in descending order, stable (:409): one thread per eigenvalue
   if (tid < FTX) sm.colsc[tid] = fmax(0.0, sm.G[tid + FTX * tid].x);
@@ -473,6 +487,224 @@ __device__ inline void fast_argmin_z(int m, int rank_one, const FastSmem<RL>& sm
   }
 }
 
+// Nuclear-norm ArgMinZ (inferLowRank_Nuclear.m:411-439) on the column-split iterate: singular-value soft
+// threshold of Z_in (n x r) by tau = 1/mu through the r x r Gram eigenproblem,
+//   Z = Z_in V diag(max(0, s - tau)/s) V',   Z_in' Z_in = V diag(s^2) V'.
+// Columns of Z_in living in peer CTAs are staged through `stage` (cap elements) in chunks of whole columns.
+// Exact screen: ||Z_in||_F <= tau  =>  every s_i <= tau  =>  Z = 0 (the usual case while mu is small).
+// Cluster syncs: 1 (screen hit) or 3 (SVT), cluster-uniform.  nrm[] = this CTA's partial norms.
+template <int RL, int CS>
+__device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<RL>& sm, int rank, double mu,
+                                             bool init_mode, double* xsc_slot, cd* stage, size_t stage_cap,
+                                             double* nrm, int* sweeps_acc) {
+  const int tid = threadIdx.x;
+  constexpr int r = RL * CS;
+  const int c0 = rank * RL;
+  const double imu = 1.0 / mu;
+  constexpr int NE = FN * RL;
+  double fro = 0.0;
+  for (int idx = tid; idx < NE; idx += NT) {
+    cd v = sm.X[idx];
+    if (!init_mode) { const cd nn = sm.N[idx]; v.x = fma(nn.x, imu, v.x); v.y = fma(nn.y, imu, v.y); }
+    sm.N[idx] = v;
+    fro += cabs2(v);
+  }
+  {
+    double v[1] = {fro};
+    block_sum<1>(v, sm.red);
+    if (tid == 0) *xsc_slot = v[0];
+  }
+  cl_sync<CS>();
+  double tot = 0.0;
+#pragma unroll
+  for (int rk = 0; rk < CS; ++rk) tot += *peer_ptr<double, CS>(xsc_slot, rk);
+  const bool all_zero = !(tot > imu * imu);      // ||Z_in||_F <= tau (NaN: falls through to the SVT)
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (all_zero && tot == tot) {
+    for (int idx = tid; idx < NE; idx += NT) {
+      if (!init_mode) {
+        const cd zo = sm.Z[idx], x = sm.X[idx], zi = sm.N[idx];
+        a0 += cabs2(x); a1 += cabs2(zo); a2 += cabs2(x);
+        sm.N[idx] = cmk(mu * zi.x, mu * zi.y);
+      } else {
+        sm.N[idx] = cmk(0.0, 0.0);
+      }
+      sm.Z[idx] = cmk(0.0, 0.0);
+    }
+  } else {
+    const int ccap = (int)(stage_cap / FN);     // whole columns per staging chunk (>= 1)
+    // ---- Gram rows of the local columns: G[c0 + cl, c'] = sum_k conj(z[k, c0+cl]) z[k, c']
+    for (int idx = tid; idx < RL * RL; idx += NT) {   // local x local
+      const int cl = idx % RL, c2 = idx / RL;
+      cd g0 = cmk(0.0, 0.0), g1 = g0, g2 = g0, g3 = g0;
+      const cd* za = sm.N + FN * cl;
+      const cd* zb = sm.N + FN * c2;
+      for (int k = 0; k < FN; k += 4) {
+        cfmac(g0, za[k], zb[k]); cfmac(g1, za[k + 1], zb[k + 1]);
+        cfmac(g2, za[k + 2], zb[k + 2]); cfmac(g3, za[k + 3], zb[k + 3]);
+      }
+      sm.xG[(c0 + cl) + r * (c0 + c2)] = cmk((g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y));
+    }
+    if constexpr (CS > 1) {
+      for (int pr = 1; pr < CS; ++pr) {
+        const int rk = (rank + pr) % CS;
+        const cd* rem = peer_ptr<cd, CS>(sm.N, rk);
+        for (int cb = 0; cb < RL; cb += ccap) {
+          const int nc = min(ccap, RL - cb);
+          __syncthreads();
+          for (int idx = tid; idx < nc * FN; idx += NT) stage[idx] = rem[(size_t)FN * cb + idx];
+          __syncthreads();
+          for (int idx = tid; idx < RL * nc; idx += NT) {
+            const int cl = idx % RL, cc = idx / RL;
+            cd g0 = cmk(0.0, 0.0), g1 = g0, g2 = g0, g3 = g0;
+            const cd* za = sm.N + FN * cl;
+            const cd* zb = stage + FN * cc;
+            for (int k = 0; k < FN; k += 4) {
+              cfmac(g0, za[k], zb[k]); cfmac(g1, za[k + 1], zb[k + 1]);
+              cfmac(g2, za[k + 2], zb[k + 2]); cfmac(g3, za[k + 3], zb[k + 3]);
+            }
+            sm.xG[(c0 + cl) + r * (rk * RL + cb + cc)] =
+                cmk((g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y));
+          }
+        }
+      }
+    }
+    cl_sync<CS>();      // every CTA's row block of G is complete
+    for (int idx = tid; idx < r * r; idx += NT) {
+      const int i = idx % r, j = idx / r;
+      const cd v = peer_ptr<cd, CS>(sm.xG, i / RL)[i + r * j];   // row i is owned by rank i / RL
+      sm.G[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += NT) {   // exact Hermitian symmetry from the lower triangle
+      const int i = idx % r, j = idx / r;
+      if (i == j) sm.G[idx].y = 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += NT) {
+      const int i = idx % r, j = idx / r;
+      if (i < j) { const cd u = sm.G[j + r * i]; sm.G[idx] = cmk(u.x, -u.y); }
+    }
+    __syncthreads();
+    int sw;
+    if constexpr (r == 20) {
+      // warm start from the previous eigenvectors (cold every 64 decompositions re-orthonormalises U)
+      const bool warm = !init_mode && (sm.ifl[2] & 63) != 0;
+      if (warm) {
+        for (int idx = tid; idx < r * r; idx += NT) {     // P <- G U
+          const int i = idx % r, j = idx / r;
+          cd t0 = cmk(0.0, 0.0), t1 = t0;
+          for (int k = 0; k < r; k += 2) {
+            cfma(t0, sm.G[i + r * k], sm.U[k + r * j]);
+            cfma(t1, sm.G[i + r * (k + 1)], sm.U[(k + 1) + r * j]);
+          }
+          sm.P[idx] = cmk(t0.x + t1.x, t0.y + t1.y);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < r * r; idx += NT) {     // G <- U' P (lower triangle, mirrored)
+          const int i = idx % r, j = idx / r;
+          if (i >= j) {
+            cd t0 = cmk(0.0, 0.0), t1 = t0;
+            for (int k = 0; k < r; k += 2) {
+              cfmac(t0, sm.U[k + r * i], sm.P[k + r * j]);
+              cfmac(t1, sm.U[(k + 1) + r * i], sm.P[(k + 1) + r * j]);
+            }
+            cd t = cmk(t0.x + t1.x, t0.y + t1.y);
+            if (i == j) t.y = 0.0;
+            sm.G[i + r * j] = t;
+            if (i != j) sm.G[j + r * i] = cmk(t.x, -t.y);
+          }
+        }
+        __syncthreads();
+      }
+      sw = jacobi_small<20>(sm.G, sm.P, sm.U, sm.pairs, !warm);
+      if (tid == 0) sm.ifl[2] += 1;
+    } else {
+      sw = jacobi_heig(sm.G, r, sm.U, r, r, true, sm.js);
+    }
+    if (tid == 0) *sweeps_acc += sw;
+    if (tid < r) {
+      const double sg = sqrt(fmax(0.0, sm.G[tid + r * tid].x));
+      sm.s2s[tid] = (sg > 0.0) ? fmax(0.0, sg - imu) / sg : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += NT) {   // P = V diag(f) V'
+      const int i = idx % r, j = idx / r;
+      cd p0 = cmk(0.0, 0.0), p1 = p0;
+      for (int k = 0; k + 1 < r; k += 2) {
+        const cd ui = sm.U[i + r * k], uj = sm.U[j + r * k];
+        const double f0 = sm.s2s[k];
+        cfmabc(p0, cmk(ui.x * f0, ui.y * f0), uj);
+        const cd vi = sm.U[i + r * (k + 1)], vj = sm.U[j + r * (k + 1)];
+        const double f1 = sm.s2s[k + 1];
+        cfmabc(p1, cmk(vi.x * f1, vi.y * f1), vj);
+      }
+      if (r & 1) {
+        const cd ui = sm.U[i + r * (r - 1)], uj = sm.U[j + r * (r - 1)];
+        const double f0 = sm.s2s[r - 1];
+        cfmabc(p0, cmk(ui.x * f0, ui.y * f0), uj);
+      }
+      sm.P[idx] = cmk(p0.x + p1.x, p0.y + p1.y);
+    }
+    __syncthreads();
+    // ---- Z[:, c0 + c'] = sum_c Z_in[:, c] P[c, c0 + c']   (thread per row k; accumulators in registers)
+    cd acc[RL];
+#pragma unroll
+    for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+    {
+      const int k = tid;
+      for (int c = 0; c < RL; ++c) {
+        const cd z = sm.N[k + FN * c];
+#pragma unroll
+        for (int c2 = 0; c2 < RL; ++c2) cfma(acc[c2], z, sm.P[(c0 + c) + r * (c0 + c2)]);
+      }
+    }
+    if constexpr (CS > 1) {
+      for (int pr = 1; pr < CS; ++pr) {
+        const int rk = (rank + pr) % CS;
+        const cd* rem = peer_ptr<cd, CS>(sm.N, rk);
+        for (int cb = 0; cb < RL; cb += ccap) {
+          const int nc = min(ccap, RL - cb);
+          __syncthreads();
+          for (int idx = tid; idx < nc * FN; idx += NT) stage[idx] = rem[(size_t)FN * cb + idx];
+          __syncthreads();
+          for (int cc = 0; cc < nc; ++cc) {
+            const cd z = stage[tid + FN * cc];
+#pragma unroll
+            for (int c2 = 0; c2 < RL; ++c2) cfma(acc[c2], z, sm.P[(rk * RL + cb + cc) + r * (c0 + c2)]);
+          }
+        }
+      }
+    }
+    cl_sync<CS>();      // peers are done reading this CTA's Z_in before it is overwritten
+    {
+      const int k = tid;
+#pragma unroll
+      for (int c = 0; c < RL; ++c) {
+        const int idx = k + FN * c;
+        const cd zn = acc[c];
+        if (!init_mode) {
+          const cd zo = sm.Z[idx], x = sm.X[idx], zi = sm.N[idx];
+          a0 += cabs2(cmk(x.x - zn.x, x.y - zn.y));
+          a1 += cabs2(cmk(zn.x - zo.x, zn.y - zo.y));
+          a2 += cabs2(x);
+          a3 += cabs2(zn);
+          sm.N[idx] = cmk(mu * (zi.x - zn.x), mu * (zi.y - zn.y));
+        } else {
+          sm.N[idx] = cmk(0.0, 0.0);
+        }
+        sm.Z[idx] = zn;
+      }
+    }
+  }
+  __syncthreads();
+  if (!init_mode) {
+    double v[4] = {a0, a1, a2, a3};
+    block_sum<4>(v, sm.red);
+    nrm[0] = v[0]; nrm[1] = v[1]; nrm[2] = v[2]; nrm[3] = v[3];
+  }
+}
+
 template <int RL, int CS>
 __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const FastDims& fd,
                                 const FastSmem<RL>& sm, cd* wsg, int rank) {
@@ -487,12 +719,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   cd* AtY = wsg + (size_t)fd.maxm * fd.maxm;   // [256 x r], column c0+c owned by this CTA
   const cd* lut = sm.lut;
   const cd* lutc = sm.lut + 4;
-  cd* scratch = sm.WT;                   // WT | AX | G | P are contiguous (U must survive: warm start)
-  // capacity is taken from this task's m (not the launch's maxm) so that the K split, hence the
-  // summation order, never depends on the batch mates
-  const size_t scratch_cap = 2 * (size_t)m * RL + 2 * FTX * FTX;
-  cd* scratch2 = sm.G;                   // G | P (for the S^-1 product, which reads WT and writes AX)
-  const size_t scratch2_cap = 2 * FTX * FTX;
+  cd* scratch = sm.WT;                   // WT | AX (pivot row / column of the Gauss-Jordan inverse)
 
   // ---- stage-local copies
   if (tid < 4) {
@@ -504,7 +731,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     sm.rows_s[i] = tk.A.rows ? tk.A.rows[i] : i;
     sm.Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
   }
-  jacobi16_tables(sm.pairs, sm.pairs + 256);
+  if (fd.nuclear && fd.r == 20) jacobi_tables<20>(sm.pairs); else jacobi_tables<FTX>(sm.pairs);
   __syncthreads();
   for (int idx = tid; idx < 16 * m; idx += NT) {
     const int w = idx / m, i = idx - w * m;
@@ -570,8 +797,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   for (int idx = tid; idx < m * RL; idx += NT) sm.M[idx] = cmk(0.0, 0.0);
   __syncthreads();
   // AX = A X  (:278)
-  prod_a<RL>(sm.cik, m, sm.X, lut, scratch, scratch_cap,
-             [&](int i, int c, cd v) { sm.AX[i + m * c] = cscale(v, cs); });
+  prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) { sm.AX[i + m * c] = cscale(v, cs); });
   // rescale so |A X| matches |B|  (:279-286)
   if (tk.sbr) {
     double v[1] = {0.0};
@@ -635,15 +861,19 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   double nz[4];
   if (tid == 0) sm.ifl[2] = 0;
   __syncthreads();
-  fast_argmin_z<RL, CS>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);   // Z = ArgMinZ(X, 0, 1)  (:288)
+  // Z = ArgMinZ(X, 0, 1)  (:288).  Nuclear staging area: WT | AX (both dead during ArgMinZ)
+  cd* stage = sm.WT;
+  const size_t stage_cap = 2 * (size_t)fd.maxm * RL;
+  if (fd.nuclear) fast_argmin_z_nuclear<RL, CS>(fd, sm, rank, 1.0, true, sm.xsc + XS_SCAL - 1, stage, stage_cap, nz, &sweeps);
+  else fast_argmin_z<RL, CS>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);
   __syncthreads();
   if (prm.need_dual) {   // AtY = A' Y  (:289)
     cd acc[RL];
 #pragma unroll
     for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-    prod_ah<RL>(sm.cki, m, sm.Y, m, lutc, acc);
+    const int kk = prod_ah<RL>(sm.cki, m, sm.Y, m, lutc, acc);
 #pragma unroll
-    for (int c = 0; c < RL; ++c) AtY[tid + (size_t)FN * (c0 + c)] = cscale(acc[c], cs);
+    for (int c = 0; c < RL; ++c) AtY[kk + (size_t)FN * (c0 + c)] = cscale(acc[c], cs);
   }
 
   double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
@@ -669,27 +899,26 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
       cd acc[RL];
 #pragma unroll
       for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
+      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
 #pragma unroll
       for (int c = 0; c < RL; ++c) {
-        const int p = tid + FN * c;
+        const int p = kk + FN * c;
         const cd z = sm.Z[p], nn = sm.N[p];
         sm.X[p] = cmk(fma(acc[c].x, cs, fma(-nn.x, imu, z.x)), fma(acc[c].y, cs, fma(-nn.y, imu, z.y)));
       }
     }
     __syncthreads();
     // ---- W = A V -> WT ; AX = S^-1 W ; X = V - A' AX   (Woodbury form of inv(A'A+I) V)
-    prod_a<RL>(sm.cik, m, sm.X, lut, scratch, scratch_cap,
-               [&](int i, int c, cd v) { sm.WT[i + m * c] = cscale(v, cs); });
-    prod_sinv<RL>(Sinv, m, sm.WT, sm.AX, scratch2, scratch2_cap);
+    prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) { sm.WT[i + m * c] = cscale(v, cs); });
+    prod_sinv<RL>(Sinv, m, sm.WT, sm.AX);
     {
       cd acc[RL];
 #pragma unroll
       for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      prod_ah<RL>(sm.cki, m, sm.AX, m, lutc, acc);
+      const int kk = prod_ah<RL>(sm.cki, m, sm.AX, m, lutc, acc);
 #pragma unroll
       for (int c = 0; c < RL; ++c) {
-        const int p = tid + FN * c;
+        const int p = kk + FN * c;
         const cd x = sm.X[p];
         sm.X[p] = cmk(fma(-acc[c].x, cs, x.x), fma(-acc[c].y, cs, x.y));
       }
@@ -701,19 +930,26 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     double pYd2 = 0.0, pJM2 = 0.0, pY2 = 0.0, pAX2 = 0.0, obj2 = 0.0, nAX2 = 0.0;
     const double i1mu = 1.0 / (1.0 + mu);
     if (tk.sbr) {
-      for (int i = tid; i < m; i += NT) {
-        double d2 = 0.0, a2 = 0.0;
-        for (int c = 0; c < RL; ++c) {
+      // thread (row i, lane-group member s): columns c = s, s + ks, ...; row sums by shuffle
+      const int ks = ksplit_for(m, 8);
+      const int i = tid / ks, s = tid - i * ks;
+      const bool act = i < m;
+      double d2 = 0.0, a2 = 0.0;
+      if (act) {
+        for (int c = s; c < RL; c += ks) {
           const cd ax = sm.AX[i + m * c], mm = sm.M[i + m * c];
           d2 += cabs2(cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y)));
           a2 += cabs2(ax);
         }
-        sm.xrow[i] = d2;
-        sm.xrow[fd.maxm + i] = a2;
       }
+      for (int o = 1; o < ks; o <<= 1) {
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (act && s == 0) { sm.xrow[i] = d2; sm.xrow[fd.maxm + i] = a2; }
       cl_sync<CS>();
-      for (int i = tid; i < m; i += NT) {
-        double d2 = 0.0, a2 = 0.0;
+      if (act) {
+        d2 = 0.0; a2 = 0.0;
 #pragma unroll
         for (int rk = 0; rk < CS; ++rk) {
           const double* pr = peer_ptr<double, CS>(sm.xrow, rk);
@@ -725,7 +961,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
         if (z) D = 1.0;
         const double f = (sm.Bs[i] / D + mu) * i1mu;
         const double isr = 1.0 / sqrt((double)r);
-        for (int c = 0; c < RL; ++c) {
+        for (int c = s; c < RL; c += ks) {
           const int p = i + m * c;
           const cd ax = sm.AX[p], mm = sm.M[p], yo = sm.Y[p];
           const cd cc = z ? cmk(isr, 0.0) : cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y));
@@ -739,9 +975,11 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
           pJM2 += cabs2(jm);
           pY2 += cabs2(yn);
         }
-        nAX2 += a2;                      // cluster totals: identical in every CTA
-        const double dd = sqrt(a2) - sm.Bs[i];
-        obj2 += dd * dd;
+        if (s == 0) {
+          nAX2 += a2;                    // cluster totals: identical in every CTA
+          const double dd = sqrt(a2) - sm.Bs[i];
+          obj2 += dd * dd;
+        }
       }
     } else {
       for (int c = warp; c < RL; c += NW) {
@@ -782,11 +1020,11 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
       cd acc[RL];
 #pragma unroll
       for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
+      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
       double v[2] = {0.0, 0.0};
 #pragma unroll
       for (int c = 0; c < RL; ++c) {
-        const size_t p = tid + (size_t)FN * (c0 + c);
+        const size_t p = kk + (size_t)FN * (c0 + c);
         const cd d = cscale(acc[c], cs);
         cd a = AtY[p];
         a.x += d.x;
@@ -802,7 +1040,12 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     if (tid == 0) sm.sc[22] += (double)(tx2 - tx1);
     // ---- Z, N update (:312, :319-320)
     // warm-started from the previous eigenvectors; a cold start every 64 iterations re-orthonormalises U
-    fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (sm.ifl[2] & 63) != 0, nz, &sweeps);
+    if (fd.nuclear) {
+      // A'(Y-Y0) has consumed WT by now; the screen scalar uses the last slot of this iteration's xsc
+      fast_argmin_z_nuclear<RL, CS>(fd, sm, rank, mu, false, xsc + XS_SCAL - 1, stage, stage_cap, nz, &sweeps);
+    } else {
+      fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (sm.ifl[2] & 63) != 0, nz, &sweeps);
+    }
     // ---- cluster-wide scalars
     if (tid == 0) {
       xsc[0] = pYd2; xsc[1] = pJM2; xsc[2] = pY2; xsc[3] = pAX2; xsc[4] = pAtYd2; xsc[5] = pAtY2;

@@ -31,9 +31,11 @@ tr = ins.train_idx[0]
 A, B, An, Bn = admm._preprocess(ins.A, ins.B, 1e-8)
 At, Bt = A[tr], B[tr]
 Xs = admm.spectral_initialize(At, Bt, 20)
-for (sbr, X0, r1, nuc) in [(True, Xs, False, False), (False, Xs, False, False), (True, Xs[:, :1], True, False),
-                           (True, Xs, False, True), (True, Xs, True, False)]:
-    for iters in (1, 2, 10, 100, 500):
+CASES = [(True, Xs, False, False), (False, Xs, False, False), (True, Xs[:, :1], True, False),
+         (True, Xs, False, True), (True, Xs, True, False), (False, Xs, False, True), (True, Xs[:, :1], False, True)]
+if len(sys.argv) > 3 and sys.argv[3] == "nuc": CASES = [c for c in CASES if c[3]]
+for (sbr, X0, r1, nuc) in CASES:
+    for iters in (1, 2, 10, 100, 300, 500):
         p = tw.Params.default(maxiter=iters, tol_rel=0.0, tol_abs=0.0)
         snap = {iters: None}
         tro = admm.StageTrace()
@@ -47,6 +49,8 @@ for (sbr, X0, r1, nuc) in [(True, Xs, False, False), (False, Xs, False, False), 
               f"| mu {W[0][0]:.6g}/{s['mu']:.6g} obj {W[0][1]:.6g}/{s['opt_obj']:.6g} optit {int(W[0][3])}/{tro.opt_iter} "
               f"col {int(W[0][4])}/{tro.opt_col} bumps {int(W[0][5])}/{tro.n_mu_bumps} sweeps {int(W[0][8])}")
 
+if len(sys.argv) > 3 and sys.argv[3] == "nuc":
+    print("fast launches:", ctx.fast_launch_count, "of", ctx.launch_count); sys.exit(0)
 # ---- 3. convergence-test mode (default tolerances)
 p = tw.Params.default()
 tro = admm.StageTrace()

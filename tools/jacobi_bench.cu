@@ -7,15 +7,15 @@
 using namespace twoace;
 __global__ void __launch_bounds__(256) kern(const cd* Gin, cd* Vout, double* evals, long long* cyc, int* sweeps, int reps) {
   __shared__ cd G[256], H[256], V[256];
-  __shared__ unsigned char pairs[256], tab[256];
-  jacobi16_tables(pairs, tab);
+  __shared__ unsigned char pairs[1280];
+  jacobi_tables<16>(pairs);
   __syncthreads();
   long long tot = 0; int sw = 0;
   for (int r = 0; r < reps; ++r) {
     G[threadIdx.x] = Gin[blockIdx.x * 256 + threadIdx.x];
     __syncthreads();
     long long t0 = clock64();
-    sw = jacobi16(G, H, V, pairs, tab, true);
+    sw = jacobi_small<16>(G, H, V, pairs, true);
     tot += clock64() - t0;
     __syncthreads();
   }

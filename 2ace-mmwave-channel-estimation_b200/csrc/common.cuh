@@ -299,8 +299,8 @@ __device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
 
 template <int D>
 __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
-                                   int max_sweeps = 30) {
-  static_assert(D % 2 == 0 && D <= 20 && D * D <= 2 * NT, "unsupported dimension");
+                                   int max_sweeps = 30, int* any_rotation = nullptr) {
+  static_assert(D % 2 == 0 && D <= 32 && D * D <= 4 * NT, "unsupported dimension");
   constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
   const unsigned char* pairs = mem;
   const unsigned char* tab = mem + JacobiTab<D>::PAIRS_BYTES;
@@ -372,11 +372,140 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
     ++sweeps;
     // quadratic convergence: a sweep whose largest rotation had |sin| <= 1e-8 leaves off-diagonals at the
     // 1e-16 level, so no verification sweep is needed (smax holds |sin|^2)
-    if (!__syncthreads_or(smax > 1.0e-16)) break;
+    const int big = __syncthreads_or(smax > 1.0e-16);
+    if (any_rotation) *any_rotation = big;     // (same value in every thread)
+    if (!big) break;
   }
   if (Gin != Ga) {   // odd number of rounds: result is in Gb
     for (int e = tid; e < E; e += NT) Ga[e] = Gb[e];
     __syncthreads();
+  }
+  return sweeps;
+}
+
+// ------------------------------------------------------------------------------------------
+// Block Jacobi for a d x d Hermitian matrix in global memory (d up to a few hundred): 16-wide index
+// blocks, round-robin over block pairs; each pair (I, J) is a 32 x 32 subproblem solved in shared memory by
+// one sweep of jacobi_small<32> (accumulating its rotation Q), after which Q is applied to the block
+// columns / rows of G and the block columns of V with small dense products.  Compared with element-wise
+// rotations on the global matrix this divides the memory traffic per sweep by ~16 (6 d^3 complex MACs per
+// sweep either way).  S, Sb, Q: shared 32 x 32 buffers; tab: JacobiTab<32>::BYTES of shared memory.
+__device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, cd* S, cd* Sb, cd* Q,
+                                        unsigned char* tab, int max_sweeps = 30) {
+  constexpr int B = 16, D2 = 2 * B;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < d * d; idx += NT) {
+    const int i = idx % d, j = idx / d;
+    V[i + (size_t)ldv * j] = cmk(i == j ? 1.0 : 0.0, 0.0);
+  }
+  jacobi_tables<D2>(tab);
+  __syncthreads();
+  const int nbk = (d + B - 1) / B;
+  if (nbk < 2) {   // single block: pad to 32 and solve directly
+    for (int e = tid; e < D2 * D2; e += NT) {
+      const int i = e % D2, j = e / D2;
+      S[e] = (i < d && j < d) ? G[i + (size_t)ldg * j] : cmk(0.0, 0.0);
+    }
+    __syncthreads();
+    const int sw = jacobi_small<D2>(S, Sb, Q, tab, true, max_sweeps);
+    for (int e = tid; e < D2 * D2; e += NT) {
+      const int i = e % D2, j = e / D2;
+      if (i < d && j < d) { G[i + (size_t)ldg * j] = S[e]; V[i + (size_t)ldv * j] = Q[e]; }
+    }
+    __syncthreads();
+    return sw;
+  }
+  const int nb2 = (nbk + 1) / 2, rounds = 2 * nb2 - 1;
+  int sweeps = 0;
+  for (; sweeps < max_sweeps; ++sweeps) {
+    int rotated = 0;
+    for (int rd = 0; rd < rounds; ++rd) {
+      for (int kb = 0; kb < nb2; ++kb) {
+        int bi, bj;
+        rr_pair(nb2, rd, kb, bi, bj);
+        if (bj >= nbk) continue;                 // dummy block (odd block count)
+        // global index of subproblem index u (0..31)
+        auto gidx = [&](int u) { return (u < B) ? bi * B + u : bj * B + (u - B); };
+        for (int e = tid; e < D2 * D2; e += NT) {
+          const int gi = gidx(e % D2), gj = gidx(e / D2);
+          S[e] = (gi < d && gj < d) ? G[gi + (size_t)ldg * gj] : cmk(0.0, 0.0);
+        }
+        __syncthreads();
+        int big = 0;
+        jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big);
+        rotated |= big;
+        // write the rotated diagonal/off-diagonal blocks back
+        for (int e = tid; e < D2 * D2; e += NT) {
+          const int gi = gidx(e % D2), gj = gidx(e / D2);
+          if (gi < d && gj < d) G[gi + (size_t)ldg * gj] = S[e];
+        }
+        // ---- columns: [G; V][:, IJ] <- [G; V][:, IJ] * Q  for the rows outside the pair (G) / all rows (V).
+        // item (row, half): 16 output columns; inputs re-read from global (L1/L2), written after a barrier
+        const int nrows = 2 * d;                  // rows of G followed by rows of V
+        for (int base = 0; base < 2 * nrows; base += NT) {
+          const int it = base + tid;
+          const bool on = it < 2 * nrows;
+          const int row = on ? (it >> 1) : 0, half = it & 1;
+          const bool isV = row >= d;
+          const int rr = isV ? row - d : row;
+          const bool skip = !on || (!isV && ((rr / B) == bi || (rr / B) == bj));   // pair rows: done in S
+          cd acc[B];
+#pragma unroll
+          for (int c = 0; c < B; ++c) acc[c] = cmk(0.0, 0.0);
+          if (!skip) {
+            const cd* M = isV ? V : G;
+            const int ld = isV ? ldv : ldg;
+            for (int u = 0; u < D2; ++u) {
+              const int gu = gidx(u);
+              if (gu >= d) continue;
+              const cd x = M[rr + (size_t)ld * gu];
+#pragma unroll
+              for (int c = 0; c < B; ++c) cfma(acc[c], x, Q[u + D2 * (half * B + c)]);
+            }
+          }
+          __syncthreads();
+          if (!skip) {
+            cd* M = isV ? V : G;
+            const int ld = isV ? ldv : ldg;
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+              const int gc = gidx(half * B + c);
+              if (gc < d) M[rr + (size_t)ld * gc] = acc[c];
+            }
+          }
+          __syncthreads();
+        }
+        // ---- rows: G[IJ, :] <- Q' * G[IJ, :]  for the columns outside the pair
+        for (int base = 0; base < 2 * d; base += NT) {
+          const int it = base + tid;
+          const bool on = it < 2 * d;
+          const int col = on ? (it >> 1) : 0, half = it & 1;
+          const bool skip = !on || (col / B) == bi || (col / B) == bj;
+          cd acc[B];
+#pragma unroll
+          for (int c = 0; c < B; ++c) acc[c] = cmk(0.0, 0.0);
+          if (!skip) {
+            for (int u = 0; u < D2; ++u) {
+              const int gu = gidx(u);
+              if (gu >= d) continue;
+              const cd x = G[gu + (size_t)ldg * col];
+#pragma unroll
+              for (int c = 0; c < B; ++c) cfmac(acc[c], Q[u + D2 * (half * B + c)], x);   // conj(Q[u, c']) * x
+            }
+          }
+          __syncthreads();
+          if (!skip) {
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+              const int gc = gidx(half * B + c);
+              if (gc < d) G[gc + (size_t)ldg * col] = acc[c];
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    if (!rotated) break;
   }
   return sweeps;
 }

@@ -6,8 +6,8 @@
 // with ArgMinX :380-388, ArgMinY :490-512, normalize_rows :517-538, ArgMinZ :402-464 and the
 // nuclear ArgMinZ of inferLowRank_Nuclear.m:411-439.  Differences from the reference formulation
 // (all exact in exact arithmetic):
-//   * inv(A'A+I) is never formed when m^2 + n*m < n^2: Woodbury  U v = v - A' S^-1 (A v),
-//     S = I + A A'  (m x m), and A X = S^-1 (A v) falls out for free.
+//   * inv(A'A+I) is never formed when m^2 + n*m < n^2: with Q = Z - N/mu, T = Y - M/mu, S = I + A A'
+//     (m x m), Woodbury gives  X = Q + A' W,  A X = T - W,  W = S^-1 (T - A Q): two A-products.
 //   * A'*Y (:309) is only computed when a tolerance is non-zero; it feeds nothing but res_dual.
 #pragma once
 #include "common.cuh"
@@ -594,34 +594,48 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
 
   for (int it = 1; it <= prm.maxiter; ++it) {
     const double imu = 1.0 / mu;
-    // ---- X update (:304, :380-388):  V = A'(Y - M/mu) + (Z - N/mu);  X = inv(A'A+I) V
-    cd* Vdst = wood ? ws.X : ws.Vb;
-    gemm_tpo(n, m, r, matAh,
-             [&](int i, int c) -> cd {
-               cd y = ws.Y[i + (size_t)m * c], mm = ws.M[i + (size_t)m * c];
-               return cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
-             },
-             [&](int k, int c, cd v) {
-               const size_t p = k + (size_t)n * c;
-               cd z = ws.Z[p], nn = ws.N[p];
-               Vdst[p] = cmk(fma(v.x, asc, fma(-nn.x, imu, z.x)), fma(v.y, asc, fma(-nn.y, imu, z.y)));
-             },
-             sm.tile, sm.big);
+    // ---- X update (:304, :380-388):  X = inv(A'A+I) (A'T + Q),  T = Y - M/mu,  Q = Z - N/mu
     if (wood) {
-      // W = A V ; AX = S^-1 W ; X = V - A' AX
+      // two-product Woodbury form:  X = Q + A' W,  A X = T - W,  W = S^-1 (T - A Q),  S = I + A A'
+      for (size_t idx = tid; idx < nr; idx += NT) {
+        const cd z = ws.Z[idx], nn = ws.N[idx];
+        ws.X[idx] = cmk(fma(-nn.x, imu, z.x), fma(-nn.y, imu, z.y));
+      }
+      __syncthreads();
       gemm_tpo(m, n, r, matA, [&](int k, int c) -> cd { return ws.X[k + (size_t)n * c]; },
-               [&](int i, int c, cd v) { ws.Wb[i + (size_t)m * c] = v; }, sm.tile, sm.big);
+               [&](int i, int c, cd v) {
+                 const size_t p = i + (size_t)m * c;
+                 const cd y = ws.Y[p], mm = ws.M[p];
+                 ws.Wb[p] = cmk(fma(-mm.x, imu, y.x) - v.x, fma(-mm.y, imu, y.y) - v.y);
+               },
+               sm.tile, sm.big);
       gemm_tpo(m, m, r, [&](int j, int i) -> cd { return ws.Sinv[i + (size_t)m * j]; },
                [&](int j, int c) -> cd { return ws.Wb[j + (size_t)m * c]; },
-               [&](int i, int c, cd v) { ws.AX[i + (size_t)m * c] = v; }, sm.tile, sm.big);
+               [&](int i, int c, cd v) { ws.AX[i + (size_t)m * c] = v; }, sm.tile, sm.big);   // W (for now)
       gemm_tpo(n, m, r, matAh, [&](int i, int c) -> cd { return ws.AX[i + (size_t)m * c]; },
                [&](int k, int c, cd v) {
                  const size_t p = k + (size_t)n * c;
-                 cd x = ws.X[p];
-                 ws.X[p] = cmk(fma(-v.x, asc, x.x), fma(-v.y, asc, x.y));
+                 const cd x = ws.X[p];
+                 ws.X[p] = cmk(fma(v.x, asc, x.x), fma(v.y, asc, x.y));
                },
                sm.tile, sm.big);
+      for (size_t idx = tid; idx < mr; idx += NT) {     // A X = T - W
+        const cd y = ws.Y[idx], mm = ws.M[idx], w = ws.AX[idx];
+        ws.AX[idx] = cmk(fma(-mm.x, imu, y.x) - w.x, fma(-mm.y, imu, y.y) - w.y);
+      }
+      __syncthreads();
     } else {
+      gemm_tpo(n, m, r, matAh,
+               [&](int i, int c) -> cd {
+                 cd y = ws.Y[i + (size_t)m * c], mm = ws.M[i + (size_t)m * c];
+                 return cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
+               },
+               [&](int k, int c, cd v) {
+                 const size_t p = k + (size_t)n * c;
+                 cd z = ws.Z[p], nn = ws.N[p];
+                 ws.Vb[p] = cmk(fma(v.x, asc, fma(-nn.x, imu, z.x)), fma(v.y, asc, fma(-nn.y, imu, z.y)));
+               },
+               sm.tile, sm.big);
       gemm_tpo(n, n, r, [&](int l, int k) -> cd { return ws.Sinv[k + (size_t)n * l]; },
                [&](int l, int c) -> cd { return ws.Vb[l + (size_t)n * c]; },
                [&](int k, int c, cd v) { ws.X[k + (size_t)n * c] = v; }, sm.tile, sm.big);

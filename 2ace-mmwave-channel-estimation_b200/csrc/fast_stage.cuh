@@ -10,7 +10,8 @@
 // unity, A_eff = cscale * u, u in {1, j, -1, -j}; two packed copies ([i-word][k] and
 // [k-word][i], 16 codes per 32-bit word) serve the A'(.) and A(.) products without a transpose.
 // Same algorithm as admm_stage.cuh (inferLowRankV4.m:260-365); differences, exact in exact arithmetic:
-//   * Woodbury form of ArgMinX (S = I + A A' from exact integer phase counts, S^-1 streamed from L2);
+//   * two-product Woodbury form of ArgMinX: X = Q + A'W, A X = T - W, W = S^-1 (T - A Q) with Q = Z - N/mu,
+//     T = Y - M/mu, S = I + A A' (from exact integer phase counts, S^-1 streamed from L2);
 //   * N is overwritten by Z_in = X + N/mu during ArgMinZ and rebuilt as N = mu (Z_in - Z)
 //     (identical to N + mu (X - Z), :319-320);
 //   * A'Y (:309) lives in global memory and is advanced by A'(Y - Y0), only when a tolerance is set;
@@ -233,9 +234,10 @@ __device__ __forceinline__ void prod_a(const uint32_t* cik, int m, const cd* V, 
   __syncthreads();
 }
 
-// out[i + m*c] = sum_j Sinv[i + m*j] * W[j + m*c]  (Sinv in global/L2)
+// W = Sinv * R (R = T - A Q in `RW`, overwritten by W) and AX = T - W (T in `TAX`, overwritten by AX).
+// Sinv lives in global memory / L2.
 template <int RL>
-__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, const cd* W, cd* out) {
+__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, cd* RW, cd* TAX) {
   const int tid = threadIdx.x;
   const int ks = ksplit_for(m, 8);
   const int i = tid / ks, s = tid - i * ks;
@@ -248,13 +250,19 @@ __device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, co
     for (int j = s; j < m; j += ks) {
       const cd a = Sinv[i + (size_t)m * j];
 #pragma unroll
-      for (int c = 0; c < RL; ++c) cfma(acc[c], a, W[j + m * c]);
+      for (int c = 0; c < RL; ++c) cfma(acc[c], a, RW[j + m * c]);
     }
   }
   group_reduce<RL>(acc, ks);
+  __syncthreads();            // every thread has finished reading R before it is overwritten by W
   if (act && s == 0) {
 #pragma unroll
-    for (int c = 0; c < RL; ++c) out[i + m * c] = acc[c];
+    for (int c = 0; c < RL; ++c) {
+      const int p = i + m * c;
+      const cd t = TAX[p];
+      RW[p] = acc[c];
+      TAX[p] = cmk(t.x - acc[c].x, t.y - acc[c].y);
+    }
   }
   __syncthreads();
 }
@@ -888,39 +896,32 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     const long long tx0 = clock64();
     double* xsc = sm.xsc + (it & 1) * XS_SCAL;
     double* xcol = sm.xcol + (it & 1) * SMALL_DMAX;
-    // ---- T = Y - M/mu  -> WT
-    for (int idx = tid; idx < m * RL; idx += NT) {
+    // ---- X update (:304, :380-388) in its two-product Woodbury form.  With Q = Z - N/mu, T = Y - M/mu and
+    // S = I + A A':   inv(A'A + I)(A'T + Q) = Q + A' W,   A X = T - W,   W = S^-1 (T - A Q)
+    for (int idx = tid; idx < m * RL; idx += NT) {       // T -> AX (becomes A X below)
       const cd y = sm.Y[idx], mm = sm.M[idx];
-      sm.WT[idx] = cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
+      sm.AX[idx] = cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
+    }
+    for (int idx = tid; idx < FN * RL; idx += NT) {      // Q -> X
+      const cd z = sm.Z[idx], nn = sm.N[idx];
+      sm.X[idx] = cmk(fma(-nn.x, imu, z.x), fma(-nn.y, imu, z.y));
     }
     __syncthreads();
-    // ---- V = A'T + (Z - N/mu)  -> X   (:383, first half)
+    prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) {     // R = T - A Q -> WT
+      const cd t = sm.AX[i + m * c];
+      sm.WT[i + m * c] = cmk(fma(-v.x, cs, t.x), fma(-v.y, cs, t.y));
+    });
+    prod_sinv<RL>(Sinv, m, sm.WT, sm.AX);                           // W -> WT, A X = T - W -> AX
     {
       cd acc[RL];
 #pragma unroll
       for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
-#pragma unroll
-      for (int c = 0; c < RL; ++c) {
-        const int p = kk + FN * c;
-        const cd z = sm.Z[p], nn = sm.N[p];
-        sm.X[p] = cmk(fma(acc[c].x, cs, fma(-nn.x, imu, z.x)), fma(acc[c].y, cs, fma(-nn.y, imu, z.y)));
-      }
-    }
-    __syncthreads();
-    // ---- W = A V -> WT ; AX = S^-1 W ; X = V - A' AX   (Woodbury form of inv(A'A+I) V)
-    prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) { sm.WT[i + m * c] = cscale(v, cs); });
-    prod_sinv<RL>(Sinv, m, sm.WT, sm.AX);
-    {
-      cd acc[RL];
-#pragma unroll
-      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      const int kk = prod_ah<RL>(sm.cki, m, sm.AX, m, lutc, acc);
+      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);  // X = Q + A' W
 #pragma unroll
       for (int c = 0; c < RL; ++c) {
         const int p = kk + FN * c;
         const cd x = sm.X[p];
-        sm.X[p] = cmk(fma(-acc[c].x, cs, x.x), fma(-acc[c].y, cs, x.y));
+        sm.X[p] = cmk(fma(acc[c].x, cs, x.x), fma(acc[c].y, cs, x.y));
       }
     }
     __syncthreads();

@@ -274,6 +274,8 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
   for (int g = 0; g < 3; ++g) {
     std::vector<StageTask>& ft = grp[g];
     if (ft.empty()) continue;
+    // longest tasks first: clusters pick tasks round-robin, so this balances the tail of the launch
+    std::stable_sort(ft.begin(), ft.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
     FastDims fd;
     fd.maxm = 1;
     for (const StageTask& t : ft) fd.maxm = std::max(fd.maxm, t.m);

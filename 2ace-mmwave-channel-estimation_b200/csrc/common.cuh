@@ -236,11 +236,14 @@ __device__ __forceinline__ void jacobi16_pairs(unsigned char* pairs) {
 // (c, sg) is renormalised in FP64 so that J is unitary to 1 ulp: n2 = c^2 + |sg|^2 = 1 + eps, |eps| ~ 1e-7,
 // 1/sqrt(n2) = 1 - eps/2 + 3 eps^2/8 (eps^3 ~ 1e-21).
 __device__ __forceinline__ void jacobi_rot_sg(double a, double cc, cd b, double floor2, double inv_g, double& c,
-                                              cd& sg) {
+                                              cd& sg, double skip_below = 0.0) {
   const double ab2 = cabs2(b);
   c = 1.0;
   sg = cmk(0.0, 0.0);
   if (!(ab2 > floor2) || !(ab2 > 1.0e-34 * fabs(a * cc)) || !(ab2 > 1e-300)) return;
+  // optional: leave a pair alone when its whole 2x2 block lies below `skip_below` (|a|, |cc|, |b| < skip):
+  // the caller does not need that part of the spectrum resolved (see the nuclear ArgMinZ)
+  if (fmax(fabs(a), fabs(cc)) < skip_below && ab2 < skip_below * skip_below) return;
   // FP32 angle on inputs normalised by g = max|diag| (inv_g = 1/g): |b|^2/g^2 lies in (1e-36, ~1] and
   // |cc - a|/g <= 2, safely inside the float range; tau = (cc - a) / (2 |b|)
   const float bxn = (float)(b.x * inv_g), byn = (float)(b.y * inv_g), dn = (float)((cc - a) * inv_g);
@@ -299,7 +302,7 @@ __device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
 
 template <int D>
 __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
-                                   int max_sweeps = 30, int* any_rotation = nullptr) {
+                                   int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0) {
   static_assert(D % 2 == 0 && D <= 32 && D * D <= 4 * NT, "unsupported dimension");
   constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
   const unsigned char* pairs = mem;
@@ -327,7 +330,7 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
       const int p = pr[2 * kp], q = pr[2 * kp + 1];
       double c;
       cd sg;
-      jacobi_rot_sg(Gin[(D + 1) * p].x, Gin[(D + 1) * q].x, Gin[p + D * q], floor2, inv_g, c, sg);
+      jacobi_rot_sg(Gin[(D + 1) * p].x, Gin[(D + 1) * q].x, Gin[p + D * q], floor2, inv_g, c, sg, skip_below);
       smax = fmax(smax, cabs2(sg));
 #pragma unroll
       for (int u = 0; u < EPT; ++u) {

@@ -625,6 +625,7 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
         }
         __syncthreads();
       }
+      // (skipping the rotations inside the sub-threshold cluster was tried: it slows convergence, measured)
       sw = jacobi_small<20>(sm.G, sm.P, sm.U, sm.pairs, !warm);
       if (tid == 0) sm.ifl[2] += 1;
     } else {
@@ -887,7 +888,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
   int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
   const int rout = tk.sbr ? r : 1;
-  if (tid == 0) { sm.sc[20] = 0.0; sm.sc[21] = 0.0; sm.sc[22] = 0.0; sm.sc[23] = 0.0; }
+  if (tid == 0) { sm.sc[20] = 0.0; sm.sc[21] = 0.0; sm.sc[22] = 0.0; sm.sc[23] = 0.0; sm.sc[24] = 0.0; }
   // sm.ifl[2] counts eigen-decompositions since the stage began (set to 0 before the :288 call)
   const long long tl0 = clock64();
 
@@ -1047,6 +1048,8 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     } else {
       fast_argmin_z<RL, CS>(m, rank_one, sm, mu, false, (sm.ifl[2] & 63) != 0, nz, &sweeps);
     }
+    const long long tx3 = clock64();
+    if (tid == 0) sm.sc[23] += (double)(tx3 - tx2);
     // ---- cluster-wide scalars
     if (tid == 0) {
       xsc[0] = pYd2; xsc[1] = pJM2; xsc[2] = pY2; xsc[3] = pAX2; xsc[4] = pAtYd2; xsc[5] = pAtY2;
@@ -1104,6 +1107,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     if (res_comb > last_res * 0.9) { mu *= prm.rho; ++bumps; }   // :358-361
     last_res = res_comb;
     __syncthreads();
+    if (tid == 0) sm.sc[24] += (double)(clock64() - tx3);
   }
   __syncthreads();
   // ---- outputs: the best iterate is already in place; all-NaN objectives give NaN (H4)
@@ -1134,7 +1138,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     tk.scal[SC_OPT_ITER] = opt_iter; tk.scal[SC_OPT_COL] = opt_col; tk.scal[SC_BUMPS] = bumps;
     tk.scal[SC_CONVERGED] = converged; tk.scal[SC_RES_COMB] = res_comb; tk.scal[SC_SWEEPS] = sweeps;
     tk.scal[9] = sm.sc[20]; tk.scal[10] = sm.sc[21]; tk.scal[11] = (double)(clock64() - tl0);
-    (void)sm.sc[22];
+    tk.scal[12] = sm.sc[22]; tk.scal[13] = sm.sc[23]; tk.scal[14] = sm.sc[24];
   }
   cl_sync<CS>();   // no CTA leaves (or reuses its exchange buffers) while a peer may still read them
 }

@@ -43,7 +43,7 @@ struct StageTask {
 
 enum {
   SC_MU = 0, SC_OPT_OBJ, SC_ITERS, SC_OPT_ITER, SC_OPT_COL, SC_BUMPS, SC_CONVERGED, SC_RES_COMB,
-  SC_SWEEPS, STAGE_SCAL = 12
+  SC_SWEEPS, STAGE_SCAL = 16
 };
 
 }  // namespace twoace

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libtwoace.so")
 MEM_HOST, MEM_DEVICE = 0, 1
 V4, V4_MULTI, NUCLEAR = 0, 1, 2
 INFO_WORDS = 16
-STAGE_WORDS = 12
+STAGE_WORDS = 16
 
 # every symbol include/twoace.h declares (checked by tests/test_abi.py)
 EXPORTS = [

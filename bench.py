@@ -244,7 +244,7 @@ def ours_arm(args, wl, rank, local_rank, world):
     Y_d = torch.empty(sum_m * 2, dtype=torch.float64, device=dev)
     q_d = torch.empty(nb, dtype=torch.float64, device=dev)
     info_d = torch.empty(nb * 16, dtype=torch.float64, device=dev)
-    sw_d = torch.empty(nb * nstage * 12, dtype=torch.float64, device=dev)
+    sw_d = torch.empty(nb * nstage * tw.lib.STAGE_WORDS, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
     def step_device():
@@ -287,7 +287,7 @@ def ours_arm(args, wl, rank, local_rank, world):
     # ---- statistics reduce (the one collective of the path), outside the timed region
     X = X_d.cpu().numpy().view(np.complex128).reshape(nb, N)
     info = info_d.cpu().numpy().reshape(nb, 16)
-    sw = sw_d.cpu().numpy().reshape(nb, nstage, 12)
+    sw = sw_d.cpu().numpy().reshape(nb, nstage, tw.lib.STAGE_WORDS)
     mse = np.array([hz.nmse(X[b], insts[b].vecH) for b in range(nb)])
     stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info), dev if world > 1 else None)
 
@@ -297,7 +297,8 @@ def ours_arm(args, wl, rank, local_rank, world):
     achieved = flops_step * args.steps / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                "kernel": "admm_stage_kernel", "kernel_ms_per_step": stage_ms / args.steps,
+                "kernel": "InferADMM stage kernels (fast_stage_kernel<RL,CS> where eligible, else admm_stage_kernel)",
+                "fast_kernel_launches": int(ctx.fast_launch_count), "kernel_ms_per_step": stage_ms / args.steps,
                 "kernel_launches_per_step": stage_launches / args.steps,
                 "kernel_share_of_step": stage_ms / ms_total,
                 "peak_source": "measured live: twoace_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 figure)",

@@ -66,10 +66,11 @@ typedef struct {
  * 7..9 per-trial quality, 10 max_quality, 11 refine iterations, 12 refine opt_iter,
  * 13 refine final mu, 14 refine mu bumps, 15 total ADMM iterations over all stages. */
 
-#define TWOACE_STAGE_WORDS 12
+#define TWOACE_STAGE_WORDS 16
 /* stage bookkeeping words (per InferADMM call): 0 mu, 1 opt_obj, 2 iters, 3 opt_iter (1-based),
  * 4 opt_col (0-based, -1 for scale_by_row), 5 mu bumps, 6 converged, 7 last res_comb,
- * 8 Jacobi sweeps, 9..11 reserved. */
+ * 8 Jacobi sweeps; 9..14 device clock cycles (fast kernel only): eigensolve, X update, whole loop,
+ * Y/M update, ArgMinZ, exchange + best-iterate tail; 15 reserved. */
 
 void twoace_default_params(twoace_params* p);
 

@@ -27,6 +27,6 @@ for rep in range(2):
     ctx.set_timing(True); ctx.timing_collect()
     _, _, _, W = sv.infer_admm_batch(As, Bs, X0, bool(sbr), False, 16, 16, p, ctx=ctx)
     ms, cnt = ctx.timing_collect()
-    if fast: print("  per-iteration kcycles: eig %.1f  xupdate %.1f  loop total %.1f  sweeps/iter %.2f" % (W[:,9].mean()/iters/1e3, W[:,10].mean()/iters/1e3, W[:,11].mean()/iters/1e3, W[:,8].mean()/iters))
+    if fast: print("  per-iteration kcycles: xupdate %.1f  yupdate %.1f  argminz %.1f (eig %.1f)  tail %.1f | loop total %.1f  sweeps/iter %.2f" % (W[:,10].mean()/iters/1e3, W[:,12].mean()/iters/1e3, W[:,13].mean()/iters/1e3, W[:,9].mean()/iters/1e3, W[:,14].mean()/iters/1e3, W[:,11].mean()/iters/1e3, W[:,8].mean()/iters))
     print(f"[fast={fast} cs={cs} fast_launches={ctx.fast_launch_count}] stage launch: nb={nb} iters={iters} r={r} sbr={sbr} M={M}: {ms:.2f} ms ({cnt} launches) -> {ms/iters*1e3:.1f} us/iter/batch, "
           f"{ms*1e-3/iters/ (nb/296.0) * 1.9e9/1e3:.0f} kcycles per iteration per CTA-slot wave")

@@ -302,7 +302,8 @@ __device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
 
 template <int D>
 __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
-                                   int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0) {
+                                   int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0,
+                                   double floor_rel = 1.0e-18) {
   static_assert(D % 2 == 0 && D <= 32 && D * D <= 4 * NT, "unsupported dimension");
   constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
   const unsigned char* pairs = mem;
@@ -315,7 +316,7 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
   double g = 0.0;
 #pragma unroll
   for (int q = 0; q < D; ++q) g = fmax(g, fabs(Ga[(D + 1) * q].x));
-  const double floor_abs = 1.0e-18 * g;
+  const double floor_abs = floor_rel * g;
   const double floor2 = floor_abs * floor_abs;
   const double inv_g = (g > 0.0) ? 1.0 / g : 0.0;
   __syncthreads();

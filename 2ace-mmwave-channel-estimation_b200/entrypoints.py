@@ -1,0 +1,124 @@
+"""Host-side mirror of the MATLAB-engine entry points that reach the ADMM solver:
+
+    [H_amp, H_angle] = channel_recovery_ADMM_v2_simulation_X(tx_ant_num, rx_ant_num, cb_amp, cb_angle,
+                                                              rss_final, seed_id)
+
+for X in {A2only, A2nuclear, multiresolution} (main/channel_recovery_ADMM_v2_simulation_*.m; called from
+main/main.py:231,308,427 through the MATLAB engine).  They are thin wrappers: dBm -> amplitude, row
+selection, the 8-value M sweep, output packing; the sweep is submitted to the CUDA library as ONE ragged
+batch in codebook mode (A is never materialised per instance).
+
+Not reproduced: MATLAB's RNG stream (randperm / randsample).  The row subsets and train
+splits are drawn from a NumPy Generator seeded with the same integer seeds, or passed explicitly.
+The `phaselift` and `directional` entry points run PhaseLift / PLOMP / PLGAMP, not ADMM,
+and are outside this build.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as _lib
+from . import solvers as _sv
+
+# channel_recovery_ADMM_v2_simulation_A2only.m:103 (40 hard-coded seeds, indexed by seed_id, 1-based)
+A2ONLY_SEEDS = [58659179, 42737934, 36326041, 89830260, 90710947, 96474890, 33424536, 67991541, 42149446,
+                38961924, 54659060, 32629256, 33087755, 27433950, 9404442, 20146383, 84040563, 75325961,
+                47726929, 13999319, 5597853, 74801351, 37024073, 75534492, 99245881, 19650488, 5314224,
+                98859252, 60803022, 76056701, 14112116, 64027813, 73073690, 6288587, 42217659, 45632040,
+                7495955, 31960297, 92863244, 93081516]
+A2NUCLEAR_SEEDS = [1024, 2048, 4096, 8192]          # …_A2nuclear.m:103
+RSS_FCT = 1e5 / 3                                    # …_A2only.m:132
+MULTIRES_THRESH = (96, 256)                          # …_multiresolution.m:111
+MULTIRES_SEPARATION = (1984, 3968, 3968)             # …_multiresolution.m:112
+
+
+def matlab_round(x):
+    """MATLAB round(): half away from zero (NumPy rounds half to even)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.sign(x) * np.floor(np.abs(x) + 0.5)
+
+
+def measurement_counts(tx_ant_num: int, rx_ant_num: int) -> np.ndarray:
+    """M = round(linspace(2, sqrt(4*Nt*Nr), 8)).^2   (…_A2only.m:106-118; main.py:67)."""
+    if not any(a in (4, 8, 16, 32, 36) for a in (tx_ant_num, rx_ant_num)):
+        raise ValueError("Number of antenna on Tx and Rx must be 4/8/16/32!")
+    return (matlab_round(np.linspace(2, np.sqrt(4 * tx_ant_num * rx_ant_num), 8)) ** 2).astype(np.int64)
+
+
+def rss_dbm_to_amplitude(rss_dbm) -> np.ndarray:
+    """sqrt(db2pow(rss) / 1000) * rss_fct   (…_A2only.m:139)."""
+    return np.sqrt(10.0 ** (np.asarray(rss_dbm, dtype=np.float64) / 10.0) / 1000.0) * RSS_FCT
+
+
+def multires_row_range(M: int):
+    """0-based half-open codebook row range of the resolution stage used for M probes
+    (…_multiresolution.m:137-143): coarse (4 antenna groups), medium (8 groups), full (16 free)."""
+    s0, s1, s2 = MULTIRES_SEPARATION
+    if M <= MULTIRES_THRESH[0]:
+        return 0, s0
+    if M <= MULTIRES_THRESH[1]:
+        return s0, s0 + s1
+    return s0 + s1, s0 + s1 + s2
+
+
+def _run(variant, tx, rx, cb_amp, cb_angle, rss_final, rng, rows=None, train_idx=None, row_range_fn=None,
+         params=None, ctx=None):
+    tx, rx = int(tx), int(rx)
+    n = tx * rx
+    cb = np.asarray(cb_amp, dtype=np.float64) * np.exp(1j * np.asarray(cb_angle, dtype=np.float64))  # :120
+    if cb.shape[1] != n:
+        raise ValueError(f"codebook has {cb.shape[1]} columns, expected tx*rx = {n}")
+    rss = np.asarray(rss_final, dtype=np.float64).reshape(-1)
+    Ms = measurement_counts(tx, rx)
+    p = params or _lib.Params.default()
+    T = 3 if variant == _lib.V4_MULTI else 1
+    if rows is None:
+        rows = []
+        for M in Ms:
+            lo, hi = (0, len(rss)) if row_range_fn is None else row_range_fn(int(M))
+            if hi > cb.shape[0] or int(M) > hi - lo:
+                raise ValueError(f"M = {M} probes requested from rows [{lo},{hi}) of a {cb.shape[0]}-row codebook")
+            rows.append((lo + rng.permutation(hi - lo)[:int(M)]).astype(np.int32))          # randperm, :137
+    if train_idx is None:
+        train_idx = [_sv.draw_train_idx(len(r), p.cc_frac, T, rng) for r in rows]
+    B = [rss_dbm_to_amplitude(rss[r]) for r in rows]                                          # :139
+    ctx = ctx or _lib.default_context()
+    ctx.set_codebook(cb)
+    res = _sv.solve_batch_codebook(variant, rows, 1.0, B, tx, rx, train_idx, p, ctx)
+    H_out = np.zeros((len(Ms), 1, n), dtype=np.complex128)                                    # Method.Number = 1
+    H_out[:, 0, :] = res.X / RSS_FCT                                                          # :170
+    H_out[np.isnan(H_out)] = 0                                                                # :176
+    return np.abs(H_out), np.angle(H_out), dict(M=Ms, rows=rows, train_idx=train_idx, result=res)
+
+
+def channel_recovery_ADMM_v2_simulation_A2only(tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, seed_id, *,
+                                               rows=None, train_idx=None, params=None, ctx=None, details=False):
+    """A2only: inferLowRankV4_multi on randperm rows of the random codebook (…_A2only.m:9-178)."""
+    rng = np.random.default_rng(A2ONLY_SEEDS[int(seed_id) - 1])
+    amp, ang, info = _run(_lib.V4_MULTI, tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, rng, rows, train_idx,
+                          None, params, ctx)
+    return (amp, ang, info) if details else (amp, ang)
+
+
+def channel_recovery_ADMM_v2_simulation_A2nuclear(tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, seed_id, *,
+                                                  rows=None, train_idx=None, params=None, ctx=None, details=False):
+    """A2nuclear: inferLowRank_Nuclear via Recover_Channel_nuclear (…_A2nuclear.m:103-104,158).  The reference
+    picks one of four seeds with an UNSEEDED randi(4) and ignores seed_id (not reproducible even in MATLAB);
+    here seed_id selects it deterministically."""
+    rng = np.random.default_rng(A2NUCLEAR_SEEDS[(int(seed_id) - 1) % 4])
+    amp, ang, info = _run(_lib.NUCLEAR, tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, rng, rows, train_idx,
+                          None, params, ctx)
+    return (amp, ang, info) if details else (amp, ang)
+
+
+def channel_recovery_ADMM_v2_simulation_multiresolution(tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final,
+                                                        seed_id, *, rows=None, train_idx=None, params=None,
+                                                        ctx=None, details=False):
+    """multiresolution: as A2only, rows drawn from the resolution stage keyed on M (…_multiresolution.m:111-143).
+    Like the reference, only defined for 16 antennas (thresh / res_separation exist only in that branch)."""
+    if int(tx_ant_num) != 16 and int(rx_ant_num) != 16:
+        raise ValueError("multiresolution is only defined for 16 antennas (thresh is undefined otherwise)")
+    rng = np.random.default_rng(A2ONLY_SEEDS[int(seed_id) - 1])
+    amp, ang, info = _run(_lib.V4_MULTI, tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, rng, rows, train_idx,
+                          multires_row_range, params, ctx)
+    return (amp, ang, info) if details else (amp, ang)

@@ -66,6 +66,7 @@ struct StageSmem {
   double* colsc;   // [SMALL_DMAX] per-column scalars
   double* sc;      // [32] broadcast scalars
   int* ifl;        // [8] broadcast ints
+  unsigned char* jtab;   // tables of jacobi_small<16> (tx == 16 only)
 };
 
 __host__ __device__ inline size_t stage_big_elems(const StageDims& d) {
@@ -85,6 +86,7 @@ __host__ __device__ inline size_t stage_smem_bytes(const StageDims& d) {
   b += 16 * NW * sizeof(double);
   b += 2 * (size_t)d.ds * sizeof(double);
   b += SMALL_DMAX * sizeof(double) + 32 * sizeof(double) + 16 * sizeof(int);
+  b += JacobiTab<16>::BYTES + 16;
   return b + 64;
 }
 
@@ -107,6 +109,7 @@ __device__ inline StageSmem carve_smem(unsigned char* p, const StageDims& d) {
   s.colsc = (double*)p;  p += SMALL_DMAX * sizeof(double);
   s.sc = (double*)p;     p += 32 * sizeof(double);
   s.ifl = (int*)p;       p += 16 * sizeof(int);
+  s.jtab = p;            p += JacobiTab<16>::BYTES;
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;
   return s;
@@ -237,9 +240,69 @@ __device__ inline void argmin_z_v4(const StageTask& tk, const StageDims& dm, con
     else if (i > j) { cd u = sm.G[j + tx * i]; sm.G[idx] = cmk(u.x, -u.y); }
   }
   __syncthreads();
-  // ---- eigen-decomposition
-  int sw = jacobi_heig(sm.G, tx, sm.U, tx, tx, true, sm.js);
+  // ---- eigen-decomposition.  tx == 16: warm start from the previous eigenvectors (kept in sm.U), exact
+  // Schur-Horn screen (if the constraints of :449-459 already hold for the sorted diagonal of U'GU they hold
+  // for the spectrum, no stage fires and Z = Z_in without any eigen-decomposition), element-form Jacobi.
+  const bool small16 = (tx == 16);
+  const bool warm = small16 && !init_mode && (sm.ifl[2] & 63) != 0;
+  bool need_eig = true;
+  if (warm) {
+    {
+      const int i = tid & 15, j = tid >> 4;
+      cd t0 = cmk(0.0, 0.0), t1 = t0;
+      for (int k = 0; k < 16; k += 2) {
+        cfma(t0, sm.G[i + 16 * k], sm.U[k + 16 * j]);
+        cfma(t1, sm.G[i + 16 * (k + 1)], sm.U[(k + 1) + 16 * j]);
+      }
+      sm.P[tid] = cmk(t0.x + t1.x, t0.y + t1.y);
+    }
+    __syncthreads();
+    {
+      const int i = tid & 15, j = tid >> 4;
+      cd t = cmk(0.0, 0.0);
+      if (i >= j) {
+        cd t0 = t, t1 = t;
+        for (int k = 0; k < 16; k += 2) {
+          cfmac(t0, sm.U[k + 16 * i], sm.P[k + 16 * j]);
+          cfmac(t1, sm.U[(k + 1) + 16 * i], sm.P[(k + 1) + 16 * j]);
+        }
+        t = cmk(t0.x + t1.x, t0.y + t1.y);
+        if (i == j) t.y = 0.0;
+      }
+      __syncthreads();
+      if (i >= j) {
+        sm.G[i + 16 * j] = t;
+        if (i != j) sm.G[j + 16 * i] = cmk(t.x, -t.y);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double dg[16], pre = 0.0, tot = 0.0;
+      for (int i = 0; i < 16; ++i) { dg[i] = fmax(0.0, sm.G[17 * i].x); tot += dg[i]; }
+      for (int i = 1; i < 16; ++i) {   // descending insertion sort
+        const double v = dg[i]; int j = i - 1;
+        while (j >= 0 && dg[j] < v) { dg[j + 1] = dg[j]; --j; }
+        dg[j + 1] = v;
+      }
+      int rl[4]; double fl[4];
+      const int ns = rank_profile_dev(tx, dm.rx, tk.m, n, rank_one, rl, fl);
+      int ok = 1, done = 0;
+      for (int k = 0; k < ns; ++k) {
+        for (; done < rl[k] && done < 16; ++done) pre += dg[done];
+        ok &= (pre >= tot * fl[k] * (1.0 + 1e-12)) ? 1 : 0;
+      }
+      sm.ifl[1] = ok;
+    }
+    __syncthreads();
+    need_eig = sm.ifl[1] == 0;
+  }
+  if (!need_eig) {
+    if (tid == 0) sm.ifl[0] = 0;
+  } else {
+  int sw = small16 ? jacobi_small<16>(sm.G, sm.P, sm.U, sm.jtab, !warm)
+                   : jacobi_heig(sm.G, tx, sm.U, tx, tx, true, sm.js);
   if (tid == 0) {
+    sm.ifl[2] += 1;
     *sweeps_acc += sw;
     // eigenvalues, clamped (:408); stable descending order (:409)
     int ord[SMALL_DMAX];
@@ -268,6 +331,7 @@ __device__ inline void argmin_z_v4(const StageTask& tk, const StageDims& dm, con
     for (int i = 0; i < tx; ++i) { if (scl[i] < 1.0) any = 1; sm.s2s[i] = sqrt(scl[i]); }
     sm.ifl[0] = any;
   }
+  }   // need_eig
   __syncthreads();
   const int any = sm.ifl[0];
   if (any) {   // P = U diag(sqrt(s2_scale)) U'   (:462)
@@ -578,6 +642,9 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   __syncthreads();
   int sweeps = 0;
   double nz[4];
+  if (tid == 0) sm.ifl[2] = 0;
+  if (dm.tx == 16) jacobi_tables<16>(sm.jtab);
+  __syncthreads();
   // Z = ArgMinZ(X, N=0, mu=1)                                                    (:288)
   if (tk.nuclear) argmin_z_nuclear(tk, dm, ws, sm, 1.0, true, nz, &sweeps);
   else argmin_z_v4(tk, dm, ws, sm, 1.0, true, rank_one, nz, &sweeps);

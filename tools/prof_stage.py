@@ -15,6 +15,8 @@ insts = hz.make_batch(nb, cb, M, 20.0)
 ctx = tw.Context(0)
 fast = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 cs = int(sys.argv[7]) if len(sys.argv) > 7 else 4
+nuc = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+mu0 = float(sys.argv[9]) if len(sys.argv) > 9 else 1e-3
 ctx.set_option("fast", fast); ctx.set_option("fast_cs", cs)
 rng = np.random.default_rng(0)
 As, Bs, X0 = [], [], []
@@ -22,10 +24,10 @@ for i in insts:
     tr = i.train_idx[0]
     As.append(i.A[tr]); Bs.append(i.B[tr] / np.linalg.norm(i.B))
     X0.append((rng.standard_normal((256, r)) + 1j * rng.standard_normal((256, r))) / 16)
-p = tw.Params.default(maxiter=iters).fixed_iters()
+p = tw.Params.default(maxiter=iters, mu0=mu0).fixed_iters()
 for rep in range(2):
     ctx.set_timing(True); ctx.timing_collect()
-    _, _, _, W = sv.infer_admm_batch(As, Bs, X0, bool(sbr), False, 16, 16, p, ctx=ctx)
+    _, _, _, W = sv.infer_admm_batch(As, Bs, X0, bool(sbr), False, 16, 16, p, nuclear=bool(nuc), ctx=ctx)
     ms, cnt = ctx.timing_collect()
     if fast: print("  per-iteration kcycles: xupdate %.1f  yupdate %.1f  argminz %.1f (eig %.1f)  tail %.1f | loop total %.1f  sweeps/iter %.2f" % (W[:,10].mean()/iters/1e3, W[:,12].mean()/iters/1e3, W[:,13].mean()/iters/1e3, W[:,9].mean()/iters/1e3, W[:,14].mean()/iters/1e3, W[:,11].mean()/iters/1e3, W[:,8].mean()/iters))
     print(f"[fast={fast} cs={cs} fast_launches={ctx.fast_launch_count}] stage launch: nb={nb} iters={iters} r={r} sbr={sbr} M={M}: {ms:.2f} ms ({cnt} launches) -> {ms/iters*1e3:.1f} us/iter/batch, "

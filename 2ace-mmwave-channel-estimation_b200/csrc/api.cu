@@ -9,6 +9,7 @@
 
 #include "../../include/twoace.h"
 #include "solve_kernels.cuh"
+#include "phaselift.cuh"
 
 using namespace twoace;
 
@@ -980,6 +981,115 @@ extern "C" int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int 
   }
   rc = launch_spectral(ctx, tasks, n, cursor); if (rc) return rc;
   rc = host_back(ctx, mem, Xs, dXs, (size_t)nb * n * r * sizeof(cd)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// PhaseLift (MyPhaseLift.m:69-107)
+extern "C" void twoace_pl_default_opts(twoace_pl_opts* o) {
+  o->maxIts = 4000; o->tol = 1e-10; o->restart = 200; o->lambda = 5e-2; o->alpha = 0.9; o->beta = 0.5;
+  o->L0 = 1.0; o->cntr_reset = 50; o->backtrack_tol = 1e-10; o->reduce = 1;
+}
+
+extern "C" int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
+                                      const int32_t* cb_rows, double row_scale, const double* y,
+                                      const twoace_pl_opts* opts, double* sig, double* info) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !m || !y || !sig) FAIL(TWOACE_E_INVALID, "null argument");
+  if (!A && !cb_rows) FAIL(TWOACE_E_INVALID, "neither dense A nor codebook rows given");
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  if (n < 1) FAIL(TWOACE_E_INVALID, "n = %d", n);
+  if (n > 256) FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift is built for n <= 256 (n = %d)", n);
+  twoace_pl_opts o;
+  if (opts) o = *opts; else twoace_pl_default_opts(&o);
+  if (o.maxIts < 1 || !(o.lambda > 0.0) || !(o.L0 > 0.0) || !(o.alpha > 0.0) || !(o.beta > 0.0) || o.restart < 1 ||
+      o.cntr_reset < 1 || !(o.tol >= 0.0))
+    FAIL(TWOACE_E_INVALID, "bad PhaseLift option (maxIts %d, lambda %g, L0 %g, alpha %g, beta %g, restart %d)",
+         o.maxIts, o.lambda, o.L0, o.alpha, o.beta, o.restart);
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (!A) {
+    if (!ctx->cb_rm) FAIL(TWOACE_E_INVALID, "no codebook registered (twoace_set_codebook)");
+    if (ctx->cb_n != n) FAIL(TWOACE_E_INVALID, "codebook has n = %d, call has n = %d", ctx->cb_n, n);
+  }
+  std::vector<size_t> a_off(nb + 1, 0), b_off(nb + 1, 0);
+  int maxm = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (m[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: m = %d", b, m[b]);
+    if (m[b] > 4096) FAIL(TWOACE_E_UNSUPPORTED, "instance %d: m = %d > 4096", b, m[b]);
+    a_off[b + 1] = a_off[b] + (size_t)m[b] * n;
+    b_off[b + 1] = b_off[b] + m[b];
+    maxm = std::max(maxm, m[b]);
+  }
+  if (!A) {
+    for (size_t i = 0; i < b_off[nb]; ++i)
+      if (cb_rows[i] < 0 || cb_rows[i] >= ctx->cb_rows) FAIL(TWOACE_E_INVALID, "codebook row id %d out of range", cb_rows[i]);
+  }
+  Staging st;
+  const void *dA = nullptr, *dY = nullptr;
+  void *dSig = nullptr, *dInfo = nullptr;
+  int rc;
+  if (A) { rc = dev_in(ctx, st, mem, A, a_off[nb] * sizeof(cd), &dA); if (rc) return rc; }
+  rc = dev_in(ctx, st, mem, y, b_off[nb] * sizeof(double), &dY); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, sig, (size_t)nb * n * sizeof(cd), &dSig); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, info, (size_t)nb * PL_INFO * sizeof(double), &dInfo); if (rc) return rc;
+
+  const size_t smem = pl_smem_bytes(n, maxm);
+  if (smem > 227 * 1024) FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift: m = %d needs %zu bytes of shared memory", maxm, smem);
+  CK(cudaFuncSetAttribute(phaselift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, phaselift_kernel, NT, smem));
+  if (per_sm < 1) FAIL(TWOACE_E_CUDA, "PhaseLift kernel does not fit on an SM");
+  // longest solves first is not knowable up front; instances are handed out dynamically through a counter
+  const int grid = std::min(nb, per_sm * ctx->num_sms);
+  const size_t ws_stride = (pl_ws_elems(n, maxm) + 15) / 16 * 16;
+  Bump bp;
+  const size_t o_ws = bp.take((size_t)grid * ws_stride * sizeof(cd));
+  const size_t o_rows = bp.take(b_off[nb] * sizeof(int32_t));
+  const size_t o_cnt = bp.take(sizeof(int));
+  rc = ensure(ctx, ctx->arena, bp.off + 256); if (rc) return rc;
+  char* base = (char*)ctx->arena.p;
+  int32_t* d_rows = (int32_t*)(base + o_rows);
+  int* d_cnt = (int*)(base + o_cnt);
+  if (!A) CK(cudaMemcpyAsync(d_rows, cb_rows, b_off[nb] * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
+  rc = ensure(ctx, ctx->taskbuf, (size_t)nb * sizeof(PlTask) + 4096); if (rc) return rc;
+  std::vector<PlTask> tasks(nb);
+  for (int b = 0; b < nb; ++b) {
+    PlTask& t = tasks[b];
+    t.A_cm = A ? (const cd*)dA + a_off[b] : nullptr;
+    t.cb = A ? nullptr : ctx->cb_rm;
+    t.rows = A ? nullptr : d_rows + b_off[b];
+    t.scale = row_scale;
+    t.y = (const double*)dY + b_off[b];
+    t.m = m[b];
+    t.sig = (cd*)dSig + (size_t)b * n;
+    t.info = dInfo ? (double*)dInfo + (size_t)b * PL_INFO : nullptr;
+  }
+  size_t cursor = 0;
+  const PlTask* dt = nullptr;
+  rc = upload_tasks(ctx, tasks, cursor, &dt); if (rc) return rc;
+  PlOpts po;
+  po.maxIts = o.maxIts; po.tol = o.tol; po.restart = o.restart; po.lam = o.lambda; po.alpha = o.alpha;
+  po.beta = o.beta; po.L0 = o.L0; po.cntr_reset = o.cntr_reset; po.backtrack_tol = o.backtrack_tol;
+  po.reduce = o.reduce;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  phaselift_kernel<<<grid, NT, smem, ctx->stream>>>(dt, nb, n, maxm, po, (cd*)(base + o_ws), ws_stride, d_cnt);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+  }
+  rc = host_back(ctx, mem, sig, dSig, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, info, dInfo, (size_t)nb * PL_INFO * sizeof(double)); if (rc) return rc;
   if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
   return TWOACE_OK;
 }

@@ -303,7 +303,7 @@ __device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
 template <int D>
 __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
                                    int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0,
-                                   double floor_rel = 1.0e-18) {
+                                   double floor_rel = 1.0e-18, double stop_sin2 = 1.0e-16) {
   static_assert(D % 2 == 0 && D <= 32 && D * D <= 4 * NT, "unsupported dimension");
   constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
   const unsigned char* pairs = mem;
@@ -376,7 +376,7 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
     ++sweeps;
     // quadratic convergence: a sweep whose largest rotation had |sin| <= 1e-8 leaves off-diagonals at the
     // 1e-16 level, so no verification sweep is needed (smax holds |sin|^2)
-    const int big = __syncthreads_or(smax > 1.0e-16);
+    const int big = __syncthreads_or(smax > stop_sin2);
     if (any_rotation) *any_rotation = big;     // (same value in every thread)
     if (!big) break;
   }
@@ -394,13 +394,19 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
 // columns / rows of G and the block columns of V with small dense products.  Compared with element-wise
 // rotations on the global matrix this divides the memory traffic per sweep by ~16 (6 d^3 complex MACs per
 // sweep either way).  S, Sb, Q: shared 32 x 32 buffers; tab: JacobiTab<32>::BYTES of shared memory.
+// Warm start: init_v == false, V holds an orthonormal basis and G = V' G0 V.  stop_sin2: a sweep whose largest
+// rotation has |sin|^2 <= stop_sin2 ends the iteration.  skip_abs2 > 0: a block pair whose off-diagonal block
+// has squared Frobenius norm <= skip_abs2 is left alone (its rotations would be below the caller's accuracy).
 __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, cd* S, cd* Sb, cd* Q,
-                                        unsigned char* tab, int max_sweeps = 30) {
+                                        unsigned char* tab, int max_sweeps = 30, bool init_v = true,
+                                        double stop_sin2 = 1.0e-16, double skip_abs2 = 0.0) {
   constexpr int B = 16, D2 = 2 * B;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < d * d; idx += NT) {
-    const int i = idx % d, j = idx / d;
-    V[i + (size_t)ldv * j] = cmk(i == j ? 1.0 : 0.0, 0.0);
+  if (init_v) {
+    for (int idx = tid; idx < d * d; idx += NT) {
+      const int i = idx % d, j = idx / d;
+      V[i + (size_t)ldv * j] = cmk(i == j ? 1.0 : 0.0, 0.0);
+    }
   }
   jacobi_tables<D2>(tab);
   __syncthreads();
@@ -411,10 +417,28 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
       S[e] = (i < d && j < d) ? G[i + (size_t)ldg * j] : cmk(0.0, 0.0);
     }
     __syncthreads();
-    const int sw = jacobi_small<D2>(S, Sb, Q, tab, true, max_sweeps);
+    const int sw = jacobi_small<D2>(S, Sb, Q, tab, true, max_sweeps, nullptr, 0.0, 1.0e-18, stop_sin2);
     for (int e = tid; e < D2 * D2; e += NT) {
       const int i = e % D2, j = e / D2;
-      if (i < d && j < d) { G[i + (size_t)ldg * j] = S[e]; V[i + (size_t)ldv * j] = Q[e]; }
+      if (i < d && j < d) G[i + (size_t)ldg * j] = S[e];
+    }
+    if (init_v) {
+      for (int e = tid; e < D2 * D2; e += NT) {
+        const int i = e % D2, j = e / D2;
+        if (i < d && j < d) V[i + (size_t)ldv * j] = Q[e];
+      }
+    } else {   // V <- V * Q (d <= 16: one row of V per thread)
+      cd row[B];
+      const bool on = tid < d;
+      if (on) {
+        for (int c = 0; c < d; ++c) {
+          cd a = cmk(0.0, 0.0);
+          for (int u = 0; u < d; ++u) cfma(a, V[tid + (size_t)ldv * u], Q[u + D2 * c]);
+          row[c] = a;
+        }
+      }
+      __syncthreads();
+      if (on) for (int c = 0; c < d; ++c) V[tid + (size_t)ldv * c] = row[c];
     }
     __syncthreads();
     return sw;
@@ -430,13 +454,23 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
         if (bj >= nbk) continue;                 // dummy block (odd block count)
         // global index of subproblem index u (0..31)
         auto gidx = [&](int u) { return (u < B) ? bi * B + u : bj * B + (u - B); };
+        double off2 = 0.0;
         for (int e = tid; e < D2 * D2; e += NT) {
-          const int gi = gidx(e % D2), gj = gidx(e / D2);
-          S[e] = (gi < d && gj < d) ? G[gi + (size_t)ldg * gj] : cmk(0.0, 0.0);
+          const int ui = e % D2, uj = e / D2;
+          const int gi = gidx(ui), gj = gidx(uj);
+          const cd v = (gi < d && gj < d) ? G[gi + (size_t)ldg * gj] : cmk(0.0, 0.0);
+          S[e] = v;
+          if (ui >= B && uj < B) off2 += cabs2(v);
         }
-        __syncthreads();
+        if (skip_abs2 > 0.0) {   // (uniform branch; contains the barrier the load needs)
+          double t[1] = {off2};
+          block_sum<1>(t, reinterpret_cast<double*>(Sb));
+          if (t[0] <= skip_abs2) continue;
+        } else {
+          __syncthreads();
+        }
         int big = 0;
-        jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big);
+        jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big, 0.0, 1.0e-18, stop_sin2);
         rotated |= big;
         // write the rotated diagonal/off-diagonal blocks back
         for (int e = tid; e < D2 * D2; e += NT) {
@@ -459,12 +493,20 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
           if (!skip) {
             const cd* M = isV ? V : G;
             const int ld = isV ? ldv : ldg;
-            for (int u = 0; u < D2; ++u) {
-              const int gu = gidx(u);
-              if (gu >= d) continue;
-              const cd x = M[rr + (size_t)ld * gu];
+            // (loads issued in groups of 8 so that their L2 latencies overlap)
+#pragma unroll 1
+            for (int u0 = 0; u0 < D2; u0 += 8) {
+              cd xv[8];
 #pragma unroll
-              for (int c = 0; c < B; ++c) cfma(acc[c], x, Q[u + D2 * (half * B + c)]);
+              for (int u = 0; u < 8; ++u) {
+                const int gu = gidx(u0 + u);
+                xv[u] = (gu < d) ? M[rr + (size_t)ld * gu] : cmk(0.0, 0.0);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int c = 0; c < B; ++c) cfma(acc[c], xv[u], Q[(u0 + u) + D2 * (half * B + c)]);
+              }
             }
           }
           __syncthreads();
@@ -489,12 +531,19 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
 #pragma unroll
           for (int c = 0; c < B; ++c) acc[c] = cmk(0.0, 0.0);
           if (!skip) {
-            for (int u = 0; u < D2; ++u) {
-              const int gu = gidx(u);
-              if (gu >= d) continue;
-              const cd x = G[gu + (size_t)ldg * col];
+#pragma unroll 1
+            for (int u0 = 0; u0 < D2; u0 += 8) {
+              cd xv[8];
 #pragma unroll
-              for (int c = 0; c < B; ++c) cfmac(acc[c], Q[u + D2 * (half * B + c)], x);   // conj(Q[u, c']) * x
+              for (int u = 0; u < 8; ++u) {
+                const int gu = gidx(u0 + u);
+                xv[u] = (gu < d) ? G[gu + (size_t)ldg * col] : cmk(0.0, 0.0);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int c = 0; c < B; ++c) cfmac(acc[c], Q[(u0 + u) + D2 * (half * B + c)], xv[u]);   // conj(Q[u, c']) * x
+              }
             }
           }
           __syncthreads();

@@ -14,6 +14,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 V4, V4_MULTI, NUCLEAR = 0, 1, 2
 INFO_WORDS = 16
 STAGE_WORDS = 16
+PL_INFO_WORDS = 16
 
 # every symbol include/twoace.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -21,7 +22,7 @@ EXPORTS = [
     "twoace_stream", "twoace_launch_count", "twoace_synchronize", "twoace_solve_batch",
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
-    "twoace_set_option", "twoace_fast_launch_count",
+    "twoace_set_option", "twoace_fast_launch_count", "twoace_pl_default_opts", "twoace_phaselift_batch",
 ]
 
 
@@ -45,6 +46,24 @@ class Params(C.Structure):
     def fixed_iters(self) -> "Params":
         q = Params(self.lam, self.r, self.mu0, self.rho, self.cc_frac, 0.0, 0.0, self.maxiter)
         return q
+
+
+class PlOpts(C.Structure):
+    """twoace_pl_opts (MyPhaseLift.m:83-92 over the tfocs_initialize.m:9-40 defaults)."""
+    _fields_ = [("maxIts", C.c_int32), ("tol", C.c_double), ("restart", C.c_int32), ("lam", C.c_double),
+                ("alpha", C.c_double), ("beta", C.c_double), ("L0", C.c_double), ("cntr_reset", C.c_int32),
+                ("backtrack_tol", C.c_double), ("reduce", C.c_int32)]
+
+    @classmethod
+    def default(cls, **kw) -> "PlOpts":
+        o = cls(4000, 1e-10, 200, 5e-2, 0.9, 0.5, 1.0, 50, 1e-10, 1)
+        for k, v in kw.items():
+            if k == "lambda_":
+                k = "lam"
+            if not hasattr(o, k):
+                raise TypeError(f"unknown PhaseLift option {k!r}")
+            setattr(o, k, v)
+        return o
 
 
 class TwoaceError(RuntimeError):
@@ -102,6 +121,11 @@ def load() -> C.CDLL:
     lib.twoace_set_option.restype = C.c_int
     lib.twoace_fast_launch_count.argtypes = [vp]
     lib.twoace_fast_launch_count.restype = C.c_int64
+    lib.twoace_pl_default_opts.argtypes = [C.POINTER(PlOpts)]
+    lib.twoace_pl_default_opts.restype = None
+    lib.twoace_phaselift_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, dp, i32p, C.c_double, dp,
+                                           C.POINTER(PlOpts), dp, dp]
+    lib.twoace_phaselift_batch.restype = C.c_int
     _lib = lib
     return lib
 
@@ -202,6 +226,10 @@ class Context:
         self.check(self.lib.twoace_infer_admm_batch(self.h, mem, nb, tx, rx, _ptr(m), _ptr(A), _ptr(B), r, _ptr(X0),
                                                     int(sbr), int(rank_one), int(nuclear), C.byref(params),
                                                     _ptr(X), _ptr(Y), _ptr(state), _ptr(words)))
+
+    def phaselift_batch_raw(self, mem, nb, n, m, A, cb_rows, row_scale, y, opts, sig, info=None):
+        self.check(self.lib.twoace_phaselift_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(cb_rows),
+                                                   float(row_scale), _ptr(y), C.byref(opts), _ptr(sig), _ptr(info)))
 
     def spectral_init_batch_raw(self, mem, nb, n, m, A, B, r, Xs):
         self.check(self.lib.twoace_spectral_init_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(B), r, _ptr(Xs)))

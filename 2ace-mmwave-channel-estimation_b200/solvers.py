@@ -22,7 +22,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import lib as _lib
-from .lib import NUCLEAR, V4, V4_MULTI, Params
+from .lib import NUCLEAR, V4, V4_MULTI, Params, PlOpts
 
 __all__ = ["inferLowRankV4", "inferLowRankV4_multi", "inferLowRank_Nuclear", "ADMM_v2", "ADMM_v2_nuclear",
            "solve_batch", "solve_batch_codebook", "infer_admm_batch", "spectral_init_batch", "BatchResult",
@@ -172,7 +172,51 @@ def spectral_init_batch(A_list, B_list, r: int, ctx: _lib.Context | None = None)
     return [Xs[b * n * r:(b + 1) * n * r].reshape(n, r, order="F").copy() for b in range(nb)]
 
 
+def phaselift_batch(A_list, y_list, opts: PlOpts | None = None, ctx: _lib.Context | None = None):
+    """Batch of MyPhaseLift solves (MyPhaseLift.m:69-107) on dense sensing matrices, ragged in m.
+    ``y_list`` holds intensities.  Returns (list of n-vectors, info array [nb, 8])."""
+    ctx = ctx or _lib.default_context()
+    nb = len(A_list)
+    if nb == 0:
+        return [], np.zeros((0, _lib.PL_INFO_WORDS))
+    n = int(np.shape(A_list[0])[1])
+    m = np.array([np.shape(a)[0] for a in A_list], dtype=np.int32)
+    A = np.ascontiguousarray(np.concatenate([np.asarray(a, np.complex128).reshape(-1, order="F") for a in A_list]))
+    y = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1) for b in y_list]))
+    if y.size != int(m.sum()):
+        raise ValueError("measurement vectors do not match the row counts of the sensing matrices")
+    sig = np.empty(nb * n, np.complex128)
+    info = np.empty((nb, _lib.PL_INFO_WORDS), np.float64)
+    ctx.phaselift_batch_raw(_lib.MEM_HOST, nb, n, m, A, None, 1.0, y, opts or PlOpts.default(), sig, info)
+    return [sig[b * n:(b + 1) * n].copy() for b in range(nb)], info
+
+
+def phaselift_batch_codebook(rows_list, row_scale: float, y_list, n: int, opts: PlOpts | None = None,
+                             ctx: _lib.Context | None = None):
+    """As phaselift_batch with sensing rows taken from the registered codebook (Context.set_codebook)."""
+    ctx = ctx or _lib.default_context()
+    nb = len(rows_list)
+    if nb == 0:
+        return [], np.zeros((0, _lib.PL_INFO_WORDS))
+    m = np.array([len(r) for r in rows_list], dtype=np.int32)
+    rows = np.ascontiguousarray(np.concatenate([np.asarray(r, np.int32).reshape(-1) for r in rows_list]))
+    y = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1) for b in y_list]))
+    if y.size != int(m.sum()):
+        raise ValueError("measurement vectors do not match the row lists")
+    sig = np.empty(nb * n, np.complex128)
+    info = np.empty((nb, _lib.PL_INFO_WORDS), np.float64)
+    ctx.phaselift_batch_raw(_lib.MEM_HOST, nb, n, m, None, rows, row_scale, y, opts or PlOpts.default(), sig, info)
+    return [sig[b * n:(b + 1) * n].copy() for b in range(nb)], info
+
+
 # ----------------------------------------------------------------------------- MATLAB-signature calls
+def MyPhaseLift(measurements, measurementMat, *, opts: PlOpts | None = None, ctx=None):
+    """recoveredSig = MyPhaseLift(measurements, measurementMat)   (MyPhaseLift.m:69)."""
+    sig, _ = phaselift_batch([np.asarray(measurementMat, np.complex128)], [np.asarray(measurements).reshape(-1)],
+                             opts, ctx)
+    return sig[0]
+
+
 def _single(variant, A, B, tx, rx, p: Params, train_idx, rng, ctx):
     A = np.asarray(A, dtype=np.complex128)
     m = A.shape[0]

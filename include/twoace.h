@@ -133,6 +133,42 @@ int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, co
 int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m,
                                const double* A, const double* B, int r, double* Xs);
 
+/* ---- PhaseLift ---------------------------------------------------------------
+ * Replaces  recoveredSig = MyPhaseLift(measurements, measurementMat)
+ * (main/src/my_recovery_algorithms/MyPhaseLift.m:69-107): trace-regularised least squares over PSD matrices,
+ *   min 0.5 || y - diag(A X A') ||^2 + lambda trace(X),  X >= 0,
+ * solved by TFOCS' Auslender-Teboulle method (solver_TraceLS.m:42, tfocs_AT.m:20-94, prox_trace.m:62-168) from
+ * X0 = 0; the result is sqrt(lambda_max) * leading eigenvector of X (global phase arbitrary, as from eig()).
+ * `y` are intensities (the squaring and the 2e5 / 1e10 scalings of Recover_Channel.m:35 are caller-side). */
+typedef struct {
+  int32_t maxIts;        /* 4000   MyPhaseLift.m:83 */
+  double tol;            /* 1e-10  MyPhaseLift.m:84 */
+  int32_t restart;       /* 200    MyPhaseLift.m:85 */
+  double lambda;         /* 5e-2   MyPhaseLift.m:92 */
+  double alpha;          /* 0.9    tfocs_initialize.m:22 */
+  double beta;           /* 0.5    tfocs_initialize.m:21 */
+  double L0;             /* 1      tfocs_initialize.m:23 */
+  int32_t cntr_reset;    /* 50     tfocs_initialize.m:31,201-207 */
+  double backtrack_tol;  /* 1e-10  tfocs_initialize.m:425 */
+  int32_t reduce;        /* 1: iterate in the row space of A when m < n (exact; see csrc/phaselift.cuh) */
+} twoace_pl_opts;
+
+void twoace_pl_default_opts(twoace_pl_opts* o);
+
+#define TWOACE_PL_INFO_WORDS 16
+/* info[b*16 + k]: 0 TFOCS iterations, 1 prox_trace evaluations (= eigendecompositions), 2 backtracking steps,
+ * 3 status (1 step-size tolerance, 2 iteration limit, 3 ||dx|| = 0, 4 NaN, 5 small step), 4 rank of the last
+ * prox output, 5 final Lipschitz estimate L, 6 dimension iterated in (m if reduced, else n), 7 lambda_max,
+ * 8 Jacobi sweeps over all eigendecompositions, 9..13 device clock cycles: gradient GEMM, warm-start transform,
+ * Jacobi, z and A(z), x update and tests; 14..15 reserved. */
+
+/* Batch of independent PhaseLift solves, ragged in m.  Sensing matrices: dense `A` (concatenated m_b x n
+ * column-major blocks) or, with A == NULL, rows `cb_rows` of the registered codebook scaled by `row_scale`.
+ * sig: nb x n complex out.  n <= 256. */
+int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
+                           const int32_t* cb_rows, double row_scale, const double* y,
+                           const twoace_pl_opts* opts, double* sig, double* info);
+
 /* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
  * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
  * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass. */

@@ -11,4 +11,5 @@ from .solvers import (ADMM_v2, ADMM_v2_nuclear, MyPhaseLift, inferLowRank_Nuclea
                       solve_batch_codebook)
 from .entrypoints import (channel_recovery_ADMM_v2_simulation_A2nuclear,  # noqa: F401
                           channel_recovery_ADMM_v2_simulation_A2only,
-                          channel_recovery_ADMM_v2_simulation_multiresolution)
+                          channel_recovery_ADMM_v2_simulation_multiresolution,
+                          channel_recovery_ADMM_v2_simulation_phaselift)

@@ -10,8 +10,8 @@ batch in codebook mode (A is never materialised per instance).
 
 Not reproduced: MATLAB's RNG stream (randperm / randsample).  The row subsets and train
 splits are drawn from a NumPy Generator seeded with the same integer seeds, or passed explicitly.
-The `phaselift` and `directional` entry points run PhaseLift / PLOMP / PLGAMP, not ADMM,
-and are outside this build.
+The `phaselift` entry point (MyPhaseLift through Recover_Channel.m:33-36) is mirrored as well; `directional`
+runs PLOMP / PLGAMP and is outside this build.
 """
 from __future__ import annotations
 
@@ -122,3 +122,36 @@ def channel_recovery_ADMM_v2_simulation_multiresolution(tx_ant_num, rx_ant_num, 
     amp, ang, info = _run(_lib.V4_MULTI, tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, rng, rows, train_idx,
                           multires_row_range, params, ctx)
     return (amp, ang, info) if details else (amp, ang)
+
+
+PHASELIFT_SEED = 4096                                # …_phaselift.m:127 (rng(4096); seed_id is ignored there)
+
+
+def channel_recovery_ADMM_v2_simulation_phaselift(tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, seed_id=1, *,
+                                                  rows=None, opts=None, ctx=None, details=False):
+    """phaselift: MyPhaseLift on randperm rows of the codebook (…_phaselift.m:9-178 -> Recover_Channel.m:33-36):
+    H = MyPhaseLift((rss_train ./ 2e5).^2 .* 1e10, beams) ./ sqrt(1e10) .* 2e5, then H ./ rss_fct.
+    The reference seeds rng(4096) regardless of seed_id."""
+    tx, rx = int(tx_ant_num), int(rx_ant_num)
+    n = tx * rx
+    cb = np.asarray(cb_amp, dtype=np.float64) * np.exp(1j * np.asarray(cb_angle, dtype=np.float64))
+    if cb.shape[1] != n:
+        raise ValueError(f"codebook has {cb.shape[1]} columns, expected tx*rx = {n}")
+    rss = np.asarray(rss_final, dtype=np.float64).reshape(-1)
+    Ms = measurement_counts(tx, rx)
+    if rows is None:
+        rng = np.random.default_rng(PHASELIFT_SEED)
+        rows = []
+        for M in Ms:
+            if int(M) > len(rss) or len(rss) > cb.shape[0]:
+                raise ValueError(f"M = {M} probes requested from {len(rss)} RSS entries / {cb.shape[0]} codebook rows")
+            rows.append(rng.permutation(len(rss))[:int(M)].astype(np.int32))                  # randperm, :132
+    y = [(rss_dbm_to_amplitude(rss[r]) / 2e5) ** 2 * 1e10 for r in rows]                      # Recover_Channel.m:35
+    ctx = ctx or _lib.default_context()
+    ctx.set_codebook(cb)
+    sig, info = _sv.phaselift_batch_codebook(rows, 1.0, y, n, opts, ctx)
+    H_out = np.zeros((len(Ms), 1, n), dtype=np.complex128)
+    H_out[:, 0, :] = np.asarray(sig) / np.sqrt(1e10) * 2e5 / RSS_FCT                          # Recover_Channel.m:35, :170
+    H_out[np.isnan(H_out)] = 0
+    amp, ang = np.abs(H_out), np.angle(H_out)
+    return (amp, ang, dict(M=Ms, rows=rows, sig=sig, info=info)) if details else (amp, ang)

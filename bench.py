@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py — ADMM CSI solves/sec (16x16 antennas, fixed iterations) on N B200s, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0|config3]
 
 A "step" is one pass of the hot path over one batch of synthetic instances (the same batch every
 step; dense inputs of a batch exceed the 126 MB L2).  Workloads (BASELINE.json configs):
   config1 (default)  inferLowRank_Nuclear, M in {32,64,128,256} x SNR in {0,10,20,30} dB
   config0            inferLowRankV4_multi (what A2only dispatches to), M=64, SNR 20 dB
-Fixed-iteration mode: tol_rel = tol_abs = 0, maxiter = 500.
+  config3            MyPhaseLift (TFOCS trace-LS, MyPhaseLift.m defaults: maxIts 4000, tol 1e-10), M=128, 20 dB
+Fixed-iteration mode (ADMM workloads): tol_rel = tol_abs = 0, maxiter = 500.
 N>1: launched under torchrun, one rank per GPU, trials sharded (weak scaling), max-over-ranks time,
 one NCCL all-reduce of the NMSE statistics tensor after the timed region.
 """
@@ -34,7 +35,11 @@ WORKLOADS = {
                     desc="config1: inferLowRank_Nuclear, 16x16, M in {32,64,128,256} x SNR in {0,10,20,30} dB"),
     "config0": dict(variant="V4_MULTI", Ms=[64], snrs=[20.0],
                     desc="config0: inferLowRankV4_multi (A2only dispatch), 16x16, M=64, SNR 20 dB"),
+    "config3": dict(variant="PHASELIFT", Ms=[128], snrs=[20.0],
+                    desc="config3: MyPhaseLift (TFOCS AT, maxIts 4000, tol 1e-10, restart 200, lambda 0.05), 16x16, "
+                         "M=128, SNR 20 dB"),
 }
+PL_METRIC = "PhaseLift CSI solves/sec (16x16 ant, M=128, MyPhaseLift.m defaults)"
 
 
 def build_instances(wl, trials_per_cell, first_trial):
@@ -360,6 +365,197 @@ def ours_arm(args, wl, rank, local_rank, world):
         print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------- PhaseLift (config 3)
+def _pl_oracle_worker(job):
+    from threadpoolctl import threadpool_limits
+    from oracle import phaselift as opl
+    A, y = job
+    with threadpool_limits(limits=1):
+        tr = opl.TfocsTrace()
+        sig = opl.my_phase_lift(y, A, None, tr)
+    return sig, tr.n_prox
+
+
+def _pl_noop(_):
+    import numpy  # noqa: F401
+    from oracle import phaselift  # noqa: F401
+    return 0
+
+
+def pl_oracle_pool(insts, cores):
+    import multiprocessing as mp
+    jobs = [(i.A, (i.B / 2.0) ** 2) for i in insts]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_pl_noop, range(cores))
+        t0 = time.perf_counter()
+        out = pool.map(_pl_oracle_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    return [o[0] for o in out], wall
+
+
+def pl_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    insts, _, _ = build_instances(wl, cores * (args.steps + args.warmup), 0)
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        pool.map(_pl_noop, range(cores))
+        for s in range(args.warmup + args.steps):
+            jobs = [(i.A, (i.B / 2.0) ** 2) for i in insts[s * cores:(s + 1) * cores]]
+            t0 = time.perf_counter()
+            pool.map(_pl_oracle_worker, jobs, chunksize=1)
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = cores / (ms * 1e-3)
+    line = {"impl": "reference", "metric": PL_METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "solves_per_step": cores,
+                       "note": "NumPy oracle (port of MyPhaseLift + TFOCS; MATLAB/Octave absent), one process per core"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} solves per step (one per core), fresh instances every step"},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def pl_ours_arm(args, wl, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = tw.Context(local_rank)
+    tpc = args.trials_per_cell
+    insts, cells, n_cells = build_instances(wl, tpc, rank * tpc)
+    nb = len(insts)
+    o = tw.PlOpts.default()
+    m = np.array([len(i.B) for i in insts], dtype=np.int32)
+    A_h = np.concatenate([i.A.reshape(-1, order="F") for i in insts])
+    y_h = np.concatenate([(i.B / 2.0) ** 2 for i in insts])            # Recover_Channel.m:35 scaling
+    W = tw.lib.PL_INFO_WORDS
+    A_d = torch.from_numpy(A_h.view(np.float64)).to(dev)
+    y_d = torch.from_numpy(y_h).to(dev)
+    sig_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
+    info_d = torch.empty(nb * W, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.phaselift_batch_raw(tw.lib.MEM_DEVICE, nb, N, m, A_d.data_ptr(), None, 1.0, y_d.data_ptr(), o,
+                                sig_d.data_ptr(), info_d.data_ptr())
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    l0 = ctx.launch_count
+    ctx.set_timing(True)
+    ctx.timing_collect()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    k_ms, k_launches = ctx.timing_collect()
+    ctx.set_timing(False)
+    launches = ctx.launch_count - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = nb * world / (ms_step * 1e-3)
+
+    sig = sig_d.cpu().numpy().view(np.complex128).reshape(nb, N)
+    info = info_d.cpu().numpy().reshape(nb, W)
+    est = 2.0 * sig                                                      # Recover_Channel.m:35: ./sqrt(1e10).*2e5
+    mse = np.array([hz.nmse(est[b], insts[b].vecH) for b in range(nb)])
+    st = torch.tensor([nb, float(mse.sum()), float(info[:, 0].sum()), float(info[:, 1].sum())], dtype=torch.float64,
+                      device=dev)
+    if world > 1:
+        dist.all_reduce(st)                                              # the one collective of the path
+    st = st.cpu().numpy()
+
+    # roofline: per prox_trace evaluation 16 m d^2 (operator + adjoint) + 36 d^3 (SURVEY §8d's F_eig), in the
+    # dimension d the kernel iterates in (row-space reduction: d = m = 128); the n = 256 contract figure beside it
+    d = info[:, 6]
+    flops_step = float(np.sum(info[:, 1] * (16.0 * m * d * d + 36.0 * d ** 3)))
+    flops_contract = float(np.sum(info[:, 1] * (16.0 * m * N * N + 36.0 * N ** 3)))
+    peak = ctx.fp64_peak_tflops()
+    achieved = flops_step * args.steps / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None, "kernel": "phaselift_kernel",
+                "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_launches / args.steps,
+                "kernel_share_of_step": k_ms / ms_total, "flops_per_step": flops_step,
+                "flops_per_step_n256_contract": flops_contract,
+                "peak_source": "measured live: twoace_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 figure)"}
+
+    A_p = torch.from_numpy(A_h.view(np.float64)).pin_memory()
+    y_p = torch.from_numpy(y_h).pin_memory()
+    sig_p = torch.empty(nb * N * 2, dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def step_host():
+        ctx.phaselift_batch_raw(tw.lib.MEM_HOST, nb, N, m, A_p.numpy(), None, 1.0, y_p.numpy(), o, sig_p.numpy(), None)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": nb * world / float(e2e_s.item()), "unit": "solves/s",
+           "h2d_bytes_per_step": int(A_p.numel() * 8 + y_p.numel() * 8),
+           "d2h_bytes_per_step": int(sig_p.numel() * 8)}
+
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sub = insts[:min(cores, nb)]
+        ref, wall = pl_oracle_pool(sub, len(sub))
+        cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": len(sub), "kind": "port",
+                        "sample": f"{len(sub)} of the step's {nb} instances, NumPy oracle, 1 BLAS thread per process, "
+                                  f"{wall:.1f} s wall"}
+        errs = [hz.aligned_rel_err(sig[k], ref[k]) for k in range(len(sub))]
+        g = hz.nmse_db([hz.nmse(est[k], sub[k].vecH) for k in range(len(sub))])
+        r = hz.nmse_db([hz.nmse(2.0 * ref[k], sub[k].vecH) for k in range(len(sub))])
+        parity = {"max_rel_err_vs_oracle": float(np.max(errs)), "frac_within_1e-4": float(np.mean(np.array(errs) <= 1e-4)),
+                  "nmse_delta_db": g - r}
+    if rank == 0:
+        line = {"metric": PL_METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "solves_per_step_per_gpu": nb,
+                           "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step); per-CTA "
+                                    "workspaces exceed L2 in aggregate",
+                           "mean_tfocs_iters": float(st[2] / st[0]), "mean_prox_evals": float(st[3] / st[0])},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "parity_sample": parity, "nmse_db": float(10 * np.log10(st[1] / st[0]))}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -374,13 +570,14 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.trials_per_cell is None:
-        args.trials_per_cell = 32 if args.workload == "config1" else 512
+        args.trials_per_cell = {"config1": 32, "config0": 512, "config3": 296}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import twoace_b200  # noqa: F401  (package import; fails loudly if the tree is broken)
+    pl = wl["variant"] == "PHASELIFT"
     if args.impl == "reference":
-        reference_arm(args, wl, rank, world)
+        (pl_reference_arm if pl else reference_arm)(args, wl, rank, world)
         return
     if world > 1:
         import torch
@@ -388,7 +585,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        ours_arm(args, wl, rank, local_rank, world)
+        (pl_ours_arm if pl else ours_arm)(args, wl, rank, local_rank, world)
     finally:
         if world > 1:
             import torch.distributed as dist

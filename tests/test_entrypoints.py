@@ -62,3 +62,28 @@ def test_a2only_and_multires_entry_points_against_oracle(gpu_ctx):
             assert hz.aligned_rel_err(H[k] * ep.RSS_FCT, Xo) < 1e-4
             n_checked += 1
     assert np.all(np.isfinite(H))                                 # NaN -> 0 (A2only.m:176)
+
+
+@pytest.mark.gpu
+def test_phaselift_entry_point_against_oracle(gpu_ctx):
+    """channel_recovery_ADMM_v2_simulation_phaselift on a 4x4-antenna 2-bit random codebook (M sweep
+    4 ... 64 probes): per-M result equals the oracle's MyPhaseLift with the scalings of Recover_Channel.m:35."""
+    import twoace_b200 as tw
+    from twoace_b200 import entrypoints as ep
+    from twoace_b200 import harness as hz
+    from oracle import phaselift as opl
+    rng = np.random.default_rng(12)
+    cb = np.exp(1j * (np.pi / 2) * rng.integers(0, 4, size=(200, 16)))
+    h = (rng.standard_normal(16) + 1j * rng.standard_normal(16)) * 1e-5
+    rss_dbm = 10 * np.log10(np.abs(cb @ h) ** 2 * 1000)
+    o = tw.PlOpts.default(maxIts=60)
+    amp, ang, info = ep.channel_recovery_ADMM_v2_simulation_phaselift(16 // 4, 4, np.abs(cb), np.angle(cb), rss_dbm, 1,
+                                                                      opts=o, ctx=gpu_ctx, details=True)
+    Ms = ep.measurement_counts(4, 4)
+    assert amp.shape == (8, 1, 16) and list(info["M"]) == list(Ms) == [4, 9, 16, 25, 25, 36, 49, 64]
+    for i, r in enumerate(info["rows"]):
+        assert len(r) == Ms[i] and len(set(r.tolist())) == Ms[i]
+        y = (ep.rss_dbm_to_amplitude(rss_dbm[r]) / 2e5) ** 2 * 1e10
+        ref = opl.my_phase_lift(y, cb[r], opl.TfocsOpts(maxIts=60)) / np.sqrt(1e10) * 2e5 / ep.RSS_FCT
+        got = amp[i, 0] * np.exp(1j * ang[i, 0])
+        assert hz.aligned_rel_err(got, ref) < 1e-6

@@ -300,10 +300,31 @@ __device__ __forceinline__ void jacobi_tables(unsigned char* mem) {
   }
 }
 
+// Tables of the "cross" ordering: H rounds, round r pairs index k of the first half with H + (k + r) % H of the
+// second half -- every (first half, second half) pair exactly once, no pair inside a half.  Used by the block
+// Jacobi for block pairs whose diagonal blocks were already swept in this sweep.
+template <int D>
+__device__ __forceinline__ void jacobi_tables_cross(unsigned char* mem) {
+  unsigned char* pairs = mem;
+  unsigned char* tab = mem + JacobiTab<D>::PAIRS_BYTES;
+  unsigned char* tab2 = tab + JacobiTab<D>::TAB_BYTES;
+  constexpr int H = D / 2;
+  for (int idx = threadIdx.x; idx < H * H; idx += NT) {
+    const int rd = idx / H, k = idx - rd * H;
+    const int p = k, q = H + (k + rd) % H;
+    pairs[2 * idx] = (unsigned char)p;
+    pairs[2 * idx + 1] = (unsigned char)q;
+    tab[D * rd + p] = (unsigned char)k;
+    tab[D * rd + q] = (unsigned char)(k | 128);
+    tab2[D * rd + p] = (unsigned char)q;
+    tab2[D * rd + q] = (unsigned char)p;
+  }
+}
+
 template <int D>
 __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* mem, bool init_v,
                                    int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0,
-                                   double floor_rel = 1.0e-18, double stop_sin2 = 1.0e-16) {
+                                   double floor_rel = 1.0e-18, double stop_sin2 = 1.0e-16, int nrounds = D - 1) {
   static_assert(D % 2 == 0 && D <= 32 && D * D <= 4 * NT, "unsupported dimension");
   constexpr int H = D / 2, E = D * D, EPT = (E + NT - 1) / NT;
   const unsigned char* pairs = mem;
@@ -326,7 +347,7 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
   int sweeps = 0;
   while (sweeps < max_sweeps) {
     double smax = 0.0;
-    for (int rd = 0; rd < D - 1; ++rd) {
+    for (int rd = 0; rd < nrounds; ++rd) {
       const unsigned char* pr = pairs + 2 * H * rd;
       const int p = pr[2 * kp], q = pr[2 * kp + 1];
       double c;
@@ -393,13 +414,15 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
 // one sweep of jacobi_small<32> (accumulating its rotation Q), after which Q is applied to the block
 // columns / rows of G and the block columns of V with small dense products.  Compared with element-wise
 // rotations on the global matrix this divides the memory traffic per sweep by ~16 (6 d^3 complex MACs per
-// sweep either way).  S, Sb, Q: shared 32 x 32 buffers; tab: JacobiTab<32>::BYTES of shared memory.
+// sweep either way).  S, Sb, Q: shared 32 x 32 buffers with Sb == S + 1024 (S | Sb also hold the padded copy of
+// Q during the updates); tab: 2 * JacobiTab<32>::BYTES of shared memory (full and cross orderings).
 // Warm start: init_v == false, V holds an orthonormal basis and G = V' G0 V.  stop_sin2: a sweep whose largest
 // rotation has |sin|^2 <= stop_sin2 ends the iteration.  skip_abs2 > 0: a block pair whose off-diagonal block
 // has squared Frobenius norm <= skip_abs2 is left alone (its rotations would be below the caller's accuracy).
 __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, cd* S, cd* Sb, cd* Q,
                                         unsigned char* tab, int max_sweeps = 30, bool init_v = true,
-                                        double stop_sin2 = 1.0e-16, double skip_abs2 = 0.0) {
+                                        double stop_sin2 = 1.0e-16, double skip_abs2 = 0.0,
+                                        long long* prof = nullptr) {
   constexpr int B = 16, D2 = 2 * B;
   const int tid = threadIdx.x;
   if (init_v) {
@@ -409,6 +432,8 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
     }
   }
   jacobi_tables<D2>(tab);
+  unsigned char* tabx = tab + JacobiTab<D2>::BYTES;
+  jacobi_tables_cross<D2>(tabx);
   __syncthreads();
   const int nbk = (d + B - 1) / B;
   if (nbk < 2) {   // single block: pad to 32 and solve directly
@@ -451,7 +476,8 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
       for (int kb = 0; kb < nb2; ++kb) {
         int bi, bj;
         rr_pair(nb2, rd, kb, bi, bj);
-        if (bj >= nbk) continue;                 // dummy block (odd block count)
+        if (bj >= nbk && rd != 0) continue;      // dummy block (odd block count); in round 0 its partner is
+                                                 // still swept internally (zero-padded second half)
         // global index of subproblem index u (0..31)
         auto gidx = [&](int u) { return (u < B) ? bi * B + u : bj * B + (u - B); };
         double off2 = 0.0;
@@ -460,7 +486,8 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
           const int gi = gidx(ui), gj = gidx(uj);
           const cd v = (gi < d && gj < d) ? G[gi + (size_t)ldg * gj] : cmk(0.0, 0.0);
           S[e] = v;
-          if (ui >= B && uj < B) off2 += cabs2(v);
+          // round 0 sweeps the whole subproblem (all pairs), the other rounds only the off-diagonal block
+          if (rd == 0 ? (ui > uj) : (ui >= B && uj < B)) off2 += cabs2(v);
         }
         if (skip_abs2 > 0.0) {   // (uniform branch; contains the barrier the load needs)
           double t[1] = {off2};
@@ -470,7 +497,12 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
           __syncthreads();
         }
         int big = 0;
-        jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big, 0.0, 1.0e-18, stop_sin2);
+        const long long tp0 = prof ? clock64() : 0;
+        // round 0 is a perfect matching of the blocks: the full 32 x 32 ordering there sweeps the pairs inside
+        // every diagonal block once per sweep; all other block pairs only need their cross pairs
+        if (rd == 0) jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big, 0.0, 1.0e-18, stop_sin2);
+        else jacobi_small<D2>(S, Sb, Q, tabx, true, 1, &big, 0.0, 1.0e-18, stop_sin2, B);
+        if (prof) prof[0] += clock64() - tp0;
         rotated |= big;
         // write the rotated diagonal/off-diagonal blocks back
         for (int e = tid; e < D2 * D2; e += NT) {
@@ -478,84 +510,104 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
           if (gi < d && gj < d) G[gi + (size_t)ldg * gj] = S[e];
         }
         // ---- columns: [G; V][:, IJ] <- [G; V][:, IJ] * Q  for the rows outside the pair (G) / all rows (V).
-        // item (row, half): 16 output columns; inputs re-read from global (L1/L2), written after a barrier
-        const int nrows = 2 * d;                  // rows of G followed by rows of V
-        for (int base = 0; base < 2 * nrows; base += NT) {
+        // item (row, quarter): row `rr` of G and row `rr` of V share every Q operand (one shared-memory load per
+        // two complex FMAs); 2 x 8 output columns.  The four quarters of a row sit in adjacent lanes: a warp-level
+        // barrier separates their loads from their stores.  Column, row and S updates touch disjoint entries, so
+        // no block barrier is needed between them.
+        constexpr int QC = B / 2;   // output columns per item: qt, qt + 4, ..., qt + 4 (QC - 1)
+        // Q re-laid with leading dimension 33 in the (now free) S | Sb area: the four lanes of a row read columns
+        // qt + 4c, i.e. four adjacent padded columns = four different bank groups (no conflict; with ld 32 every
+        // column of Q starts in bank 0)
+        constexpr int LDQ = D2 + 1;
+        cd* Qp = S;
+        __syncthreads();
+        for (int e = tid; e < D2 * D2; e += NT) Qp[(e % D2) + LDQ * (e / D2)] = Q[e];
+        __syncthreads();
+        for (int base = 0; base < 4 * d; base += NT) {
           const int it = base + tid;
-          const bool on = it < 2 * nrows;
-          const int row = on ? (it >> 1) : 0, half = it & 1;
-          const bool isV = row >= d;
-          const int rr = isV ? row - d : row;
-          const bool skip = !on || (!isV && ((rr / B) == bi || (rr / B) == bj));   // pair rows: done in S
-          cd acc[B];
+          const bool on = it < 4 * d;
+          const int rr = on ? (it >> 2) : 0, qt = it & 3;
+          const bool doG = on && !((rr / B) == bi || (rr / B) == bj);   // pair rows of G: done in S
+          cd accg[QC], accv[QC];
 #pragma unroll
-          for (int c = 0; c < B; ++c) acc[c] = cmk(0.0, 0.0);
-          if (!skip) {
-            const cd* M = isV ? V : G;
-            const int ld = isV ? ldv : ldg;
-            // (loads issued in groups of 8 so that their L2 latencies overlap)
+          for (int c = 0; c < QC; ++c) { accg[c] = cmk(0.0, 0.0); accv[c] = cmk(0.0, 0.0); }
+          if (on) {
 #pragma unroll 1
             for (int u0 = 0; u0 < D2; u0 += 8) {
-              cd xv[8];
+              cd xg[8], xv[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const int gu = gidx(u0 + u);
-                xv[u] = (gu < d) ? M[rr + (size_t)ld * gu] : cmk(0.0, 0.0);
+                xg[u] = (doG && gu < d) ? G[rr + (size_t)ldg * gu] : cmk(0.0, 0.0);
+                xv[u] = (gu < d) ? V[rr + (size_t)ldv * gu] : cmk(0.0, 0.0);
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
 #pragma unroll
-                for (int c = 0; c < B; ++c) cfma(acc[c], xv[u], Q[(u0 + u) + D2 * (half * B + c)]);
+                for (int c = 0; c < QC; ++c) {
+                  const cd q = Qp[(u0 + u) + LDQ * (qt + 4 * c)];
+                  cfma(accg[c], xg[u], q);
+                  cfma(accv[c], xv[u], q);
+                }
               }
             }
           }
-          __syncthreads();
-          if (!skip) {
-            cd* M = isV ? V : G;
-            const int ld = isV ? ldv : ldg;
+          __syncwarp();
+          if (on) {
 #pragma unroll
-            for (int c = 0; c < B; ++c) {
-              const int gc = gidx(half * B + c);
-              if (gc < d) M[rr + (size_t)ld * gc] = acc[c];
+            for (int c = 0; c < QC; ++c) {
+              const int gc = gidx(qt + 4 * c);
+              if (gc < d) {
+                if (doG) G[rr + (size_t)ldg * gc] = accg[c];
+                V[rr + (size_t)ldv * gc] = accv[c];
+              }
             }
           }
-          __syncthreads();
         }
-        // ---- rows: G[IJ, :] <- Q' * G[IJ, :]  for the columns outside the pair
-        for (int base = 0; base < 2 * d; base += NT) {
+        // ---- rows: G[IJ, :] <- Q' * G[IJ, :]  for the columns outside the pair; item (column pair, quarter):
+        // columns `col` and `col + hc` share the Q operands
+        const int hc = (d + 1) / 2;
+        for (int base = 0; base < 4 * hc; base += NT) {
           const int it = base + tid;
-          const bool on = it < 2 * d;
-          const int col = on ? (it >> 1) : 0, half = it & 1;
-          const bool skip = !on || (col / B) == bi || (col / B) == bj;
-          cd acc[B];
+          const bool on = it < 4 * hc;
+          const int c0 = on ? (it >> 2) : 0, c1 = c0 + hc, qt = it & 3;
+          const bool do0 = on && !((c0 / B) == bi || (c0 / B) == bj);
+          const bool do1 = on && c1 < d && !((c1 / B) == bi || (c1 / B) == bj);
+          cd acc0[QC], acc1[QC];
 #pragma unroll
-          for (int c = 0; c < B; ++c) acc[c] = cmk(0.0, 0.0);
-          if (!skip) {
+          for (int c = 0; c < QC; ++c) { acc0[c] = cmk(0.0, 0.0); acc1[c] = cmk(0.0, 0.0); }
+          if (do0 || do1) {
 #pragma unroll 1
             for (int u0 = 0; u0 < D2; u0 += 8) {
-              cd xv[8];
+              cd x0[8], x1[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const int gu = gidx(u0 + u);
-                xv[u] = (gu < d) ? G[gu + (size_t)ldg * col] : cmk(0.0, 0.0);
+                x0[u] = (do0 && gu < d) ? G[gu + (size_t)ldg * c0] : cmk(0.0, 0.0);
+                x1[u] = (do1 && gu < d) ? G[gu + (size_t)ldg * c1] : cmk(0.0, 0.0);
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
 #pragma unroll
-                for (int c = 0; c < B; ++c) cfmac(acc[c], Q[(u0 + u) + D2 * (half * B + c)], xv[u]);   // conj(Q[u, c']) * x
+                for (int c = 0; c < QC; ++c) {
+                  const cd q = Qp[(u0 + u) + LDQ * (qt + 4 * c)];
+                  cfmac(acc0[c], q, x0[u]);   // conj(Q[u, c']) * x
+                  cfmac(acc1[c], q, x1[u]);
+                }
               }
             }
           }
-          __syncthreads();
-          if (!skip) {
+          __syncwarp();
 #pragma unroll
-            for (int c = 0; c < B; ++c) {
-              const int gc = gidx(half * B + c);
-              if (gc < d) G[gc + (size_t)ldg * col] = acc[c];
+          for (int c = 0; c < QC; ++c) {
+            const int gc = gidx(qt + 4 * c);
+            if (gc < d) {
+              if (do0) G[gc + (size_t)ldg * c0] = acc0[c];
+              if (do1) G[gc + (size_t)ldg * c1] = acc1[c];
             }
           }
-          __syncthreads();
         }
+        __syncthreads();
       }
     }
     if (!rotated) break;

@@ -47,7 +47,8 @@ struct PlTask {
 };
 
 constexpr int PL_INFO = 16;  // niter, n_prox, n_backtracks, status, rank, L, d, lambda_max, Jacobi sweeps,
-                             // cycles: gradient GEMM, warm transform, Jacobi, z / A_z, x update + tests; 14-15 reserved
+                             // cycles: gradient GEMM, warm transform, Jacobi, z / A_z, x update + tests, subproblem solves
+                             // (part of Jacobi); 15 reserved
 enum { PL_ST_TOL = 1, PL_ST_MAXIT = 2, PL_ST_DX0 = 3, PL_ST_NAN = 4, PL_ST_SMALLSTEP = 5 };
 
 constexpr int PG_TM = 64, PG_TK = 8, PG_LD = PG_TM + 1;
@@ -129,7 +130,7 @@ struct PlSmem {
 __host__ __device__ inline size_t pl_smem_bytes(int n, int maxm) {
   size_t b = 0;
   b += 3 * 32 * 32 * sizeof(cd);
-  b += JacobiTab<32>::BYTES;
+  b += 2 * JacobiTab<32>::BYTES;
   b += 7 * (size_t)((maxm + 1) / 2 * 2) * sizeof(double);
   b += (size_t)n * sizeof(double) + (size_t)n * sizeof(int);
   b += 4 * NW * sizeof(double) + 16 * sizeof(int);
@@ -144,7 +145,7 @@ __device__ inline PlSmem pl_carve(unsigned char* p, int n, int maxm) {
   s.Q = reinterpret_cast<cd*>(p);  p += 32 * 32 * sizeof(cd);
   s.sA = s.Sb;   // the GEMM tiles (520 elements each) alias two Jacobi buffers: never live at the same time
   s.sB = s.Q;
-  s.tab = p;                       p += JacobiTab<32>::BYTES;
+  s.tab = p;                       p += 2 * JacobiTab<32>::BYTES;
   double* dp = reinterpret_cast<double*>(p);
   s.b = dp; s.Ax = dp + mv; s.Az = dp + 2 * mv; s.Ay = dp + 3 * mv; s.Axo = dp + 4 * mv; s.Azo = dp + 5 * mv;
   s.g = dp + 6 * mv;
@@ -226,7 +227,8 @@ __device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const Pl
   __syncthreads();
   const double skip = 1.0e-13 * gm;
   const long long t1 = clock64();
-  const int sw = block_jacobi_heig(W, d, V, d, d, sm.S, sm.Sb, sm.Q, sm.tab, 30, false, 1.0e-12, skip * skip);
+  const int sw = block_jacobi_heig(W, d, V, d, d, sm.S, sm.Sb, sm.Q, sm.tab, 30, false, 1.0e-12, skip * skip,
+                                   tc ? tc + 4 : nullptr);
   if (tc) { tc[0] += t1 - t0; tc[1] += clock64() - t1; }
   return sw;
 }
@@ -324,7 +326,7 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
   bool backtrack_simple = true;
   int backtrack_steps = 0, restart_iter = 0, n_iter = 0, status = 0;
   int n_prox = 0, n_bt = 0, rank = 0;
-  long long tc[5] = {0, 0, 0, 0, 0}, n_sweeps = 0;
+  long long tc[6] = {0, 0, 0, 0, 0, 0}, n_sweeps = 0;   // [5]: cycles inside the 32 x 32 subproblem solves
   double xy_sq = 0.0;
 
   while (true) {                                                     // tfocs_AT.m:20
@@ -574,7 +576,7 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
     tk.info[4] = rank; tk.info[5] = L; tk.info[6] = d; tk.info[7] = lbest;
     tk.info[8] = (double)n_sweeps;
     for (int q = 0; q < 5; ++q) tk.info[9 + q] = (double)tc[q];
-    tk.info[14] = 0.0; tk.info[15] = 0.0;
+    tk.info[14] = (double)tc[5]; tk.info[15] = 0.0;
   }
   __syncthreads();
 }

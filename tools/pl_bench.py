@@ -27,3 +27,4 @@ print(f"nb {nb} M {M}: kernel {ms:.0f} ms wall {wall:.2f}s -> {nb / (ms / 1e3):.
 cyc = info[:, 9:14].sum(axis=0)
 print("cycle shares: grad %.3f warm %.3f jacobi %.3f z/Az %.3f x/tests %.3f; cycles per prox %.0f; sweeps per prox %.2f" % (
     *(cyc / cyc.sum()), cyc.sum() / nprox, info[:, 8].sum() / nprox))
+print("subproblem solves: %.3f of Jacobi cycles" % (info[:, 14].sum() / info[:, 11].sum()))

@@ -415,14 +415,17 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
 // columns / rows of G and the block columns of V with small dense products.  Compared with element-wise
 // rotations on the global matrix this divides the memory traffic per sweep by ~16 (6 d^3 complex MACs per
 // sweep either way).  S, Sb, Q: shared 32 x 32 buffers with Sb == S + 1024 (S | Sb also hold the padded copy of
-// Q during the updates); tab: 2 * JacobiTab<32>::BYTES of shared memory (full and cross orderings).
+// Q during the updates); tab: 2 * JacobiTab<32>::BYTES + 64 bytes of shared memory (full and cross orderings,
+// block flags).  act_thr: after the first sweep only block pairs that contain a diagonal entry > act_thr are
+// processed (the caller only needs the eigenpairs above that threshold resolved to full accuracy; the others
+// stay at the accuracy one sweep gives, which keeps the basis a good warm start).
 // Warm start: init_v == false, V holds an orthonormal basis and G = V' G0 V.  stop_sin2: a sweep whose largest
 // rotation has |sin|^2 <= stop_sin2 ends the iteration.  skip_abs2 > 0: a block pair whose off-diagonal block
 // has squared Frobenius norm <= skip_abs2 is left alone (its rotations would be below the caller's accuracy).
 __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, cd* S, cd* Sb, cd* Q,
                                         unsigned char* tab, int max_sweeps = 30, bool init_v = true,
                                         double stop_sin2 = 1.0e-16, double skip_abs2 = 0.0,
-                                        long long* prof = nullptr) {
+                                        long long* prof = nullptr, double act_thr = -INFINITY) {
   constexpr int B = 16, D2 = 2 * B;
   const int tid = threadIdx.x;
   if (init_v) {
@@ -469,13 +472,22 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
     return sw;
   }
   const int nb2 = (nbk + 1) / 2, rounds = 2 * nb2 - 1;
+  int* imp = reinterpret_cast<int*>(tab + 2 * JacobiTab<D2>::BYTES);   // [16] block holds an entry > act_thr
   int sweeps = 0;
   for (; sweeps < max_sweeps; ++sweeps) {
     int rotated = 0;
+    if (sweeps > 0 && act_thr > -INFINITY) {
+      if (tid < 16) imp[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < d; i += NT)
+        if (G[i + (size_t)ldg * i].x > act_thr) imp[i / B] = 1;
+      __syncthreads();
+    }
     for (int rd = 0; rd < rounds; ++rd) {
       for (int kb = 0; kb < nb2; ++kb) {
         int bi, bj;
         rr_pair(nb2, rd, kb, bi, bj);
+        if (sweeps > 0 && act_thr > -INFINITY && !(imp[bi] || (bj < nbk && imp[bj]))) continue;
         if (bj >= nbk && rd != 0) continue;      // dummy block (odd block count); in round 0 its partner is
                                                  // still swept internally (zero-padded second half)
         // global index of subproblem index u (0..31)

@@ -19,7 +19,9 @@
 //  * A(z) = sum_k s_k |A v_k|^2 over the kept eigenpairs instead of diag(A z A').
 //  * eig(): two-sided block Jacobi warm-started from the previous eigenbasis U (G = U' W U), stopped when the
 //    largest rotation of a sweep has |sin| <= 1e-6 (off-diagonals then <= 1e-12 |W|: the prox is non-expansive,
-//    errors do not accumulate beyond that level).
+//    errors do not accumulate beyond that level).  Only eigenpairs above lambda*t enter the prox, so after the
+//    first (full) sweep the later sweeps are restricted to block pairs holding a diagonal entry above that
+//    threshold; the kept eigenvectors are moved to the leading columns so that this is one block row.
 #pragma once
 #include "common.cuh"
 
@@ -130,7 +132,7 @@ struct PlSmem {
 __host__ __device__ inline size_t pl_smem_bytes(int n, int maxm) {
   size_t b = 0;
   b += 3 * 32 * 32 * sizeof(cd);
-  b += 2 * JacobiTab<32>::BYTES;
+  b += 2 * JacobiTab<32>::BYTES + 64;
   b += 7 * (size_t)((maxm + 1) / 2 * 2) * sizeof(double);
   b += (size_t)n * sizeof(double) + (size_t)n * sizeof(int);
   b += 4 * NW * sizeof(double) + 16 * sizeof(int);
@@ -145,7 +147,7 @@ __device__ inline PlSmem pl_carve(unsigned char* p, int n, int maxm) {
   s.Q = reinterpret_cast<cd*>(p);  p += 32 * 32 * sizeof(cd);
   s.sA = s.Sb;   // the GEMM tiles (520 elements each) alias two Jacobi buffers: never live at the same time
   s.sB = s.Q;
-  s.tab = p;                       p += 2 * JacobiTab<32>::BYTES;
+  s.tab = p;                       p += 2 * JacobiTab<32>::BYTES + 64;
   double* dp = reinterpret_cast<double*>(p);
   s.b = dp; s.Ax = dp + mv; s.Az = dp + 2 * mv; s.Ay = dp + 3 * mv; s.Axo = dp + 4 * mv; s.Azo = dp + 5 * mv;
   s.g = dp + 6 * mv;
@@ -200,7 +202,8 @@ __device__ inline void lifted_forward(const cd* At, int m, int d, const cd* M, c
 
 // Hermitian eigendecomposition W = V diag(lam) V' warm-started from the basis U.  W is overwritten by the
 // rotated matrix (eigenvalues on its diagonal); V receives the eigenvectors.  T: d x d scratch.
-__device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const PlSmem& sm, long long* tc = nullptr) {
+__device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const PlSmem& sm, long long* tc = nullptr,
+                               double act_thr = -INFINITY) {
   const int tid = threadIdx.x;
   const long long t0 = clock64();
   // T = W U
@@ -228,7 +231,7 @@ __device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const Pl
   const double skip = 1.0e-13 * gm;
   const long long t1 = clock64();
   const int sw = block_jacobi_heig(W, d, V, d, d, sm.S, sm.Sb, sm.Q, sm.tab, 30, false, 1.0e-12, skip * skip,
-                                   tc ? tc + 4 : nullptr);
+                                   tc ? tc + 4 : nullptr, act_thr > -INFINITY ? act_thr - 1.0e-6 * gm : act_thr);
   if (tc) { tc[0] += t1 - t0; tc[1] += clock64() - t1; }
   return sw;
 }
@@ -385,7 +388,7 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
       cd* V = ws.U[uc ^ 1];
       long long t1 = clock64();
       tc[0] += t1 - t0;
-      n_sweeps += warm_eig(ws.W, ws.U[uc], V, ws.T, d, sm, &tc[1]);  // prox_trace.m:92
+      n_sweeps += warm_eig(ws.W, ws.U[uc], V, ws.T, d, sm, &tc[1], tau);   // prox_trace.m:92
       uc ^= 1;
       t0 = clock64();
       n_prox++;
@@ -414,6 +417,23 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
       for (int k = tid; k < kact; k += NT) sm.sv[k] = ws.W[sm.idx[k] + (size_t)d * sm.idx[k]].x - tau;
       __syncthreads();
       rank = kact;
+      // keep the kept eigenvectors in the leading columns of the basis (column order is free): the next warm
+      // start then finds every entry above the threshold in block 0 and its later sweeps touch 7 of 28 block pairs
+      if (kact <= 16) {
+        for (int a = 0; a < kact; ++a) {
+          const int c = sm.idx[a];                     // (ascending, so c >= a and column c has not moved yet)
+          if (c != a) {
+            for (int i = tid; i < d; i += NT) {
+              const cd t = V[i + (size_t)d * a];
+              V[i + (size_t)d * a] = V[i + (size_t)d * c];
+              V[i + (size_t)d * c] = t;
+            }
+          }
+        }
+        __syncthreads();
+        for (int a = tid; a < kact; a += NT) sm.idx[a] = a;
+        __syncthreads();
+      }
       // z = V_+ diag(s) V_+'                                          (prox_trace.m:147-149)
       if (kact == 0) {
         for (size_t e = tid; e < dd; e += NT) ZN[e] = cmk(0.0, 0.0);

@@ -108,7 +108,7 @@ __host__ __device__ inline size_t spec_smem_bytes(const SpecDims& d) {
   b += (size_t)(d.dmax / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));           // jacobi
   b += (size_t)d.dmax * (sizeof(double) + sizeof(int));                        // s2, order
   b += 16 * NW * sizeof(double) + 64;
-  b += 3 * 1024 * sizeof(cd) + 2 * JacobiTab<32>::BYTES + 32;                  // block Jacobi buffers
+  b += 3 * 1024 * sizeof(cd) + 2 * JacobiTab<32>::BYTES + 64 + 32;             // block Jacobi buffers
   return b + 64;
 }
 
@@ -135,7 +135,7 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
   js.flag = (int*)p;          p += 8;
   p = (unsigned char*)(((uintptr_t)p + 15) / 16 * 16);
   cd* bjS = (cd*)p;           p += 3 * 1024 * sizeof(cd);          // S, Sb, Q of the block Jacobi
-  unsigned char* bjTab = p;   p += 2 * JacobiTab<32>::BYTES;
+  unsigned char* bjTab = p;   p += 2 * JacobiTab<32>::BYTES + 64;
 
   cd* ws = wsbase + (size_t)blockIdx.x * dm.ws_stride;
   cd* Acm = ws;

@@ -418,14 +418,16 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
 // Q during the updates); tab: 2 * JacobiTab<32>::BYTES + 64 bytes of shared memory (full and cross orderings,
 // block flags).  act_thr: after the first sweep only block pairs that contain a diagonal entry > act_thr are
 // processed (the caller only needs the eigenpairs above that threshold resolved to full accuracy; the others
-// stay at the accuracy one sweep gives, which keeps the basis a good warm start).
+// stay at the accuracy one sweep gives, which keeps the basis a good warm start); in the first sweep such pairs
+// are skipped when their off-diagonal block is below skip_loose2 (squared Frobenius norm).
 // Warm start: init_v == false, V holds an orthonormal basis and G = V' G0 V.  stop_sin2: a sweep whose largest
 // rotation has |sin|^2 <= stop_sin2 ends the iteration.  skip_abs2 > 0: a block pair whose off-diagonal block
 // has squared Frobenius norm <= skip_abs2 is left alone (its rotations would be below the caller's accuracy).
 __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, cd* S, cd* Sb, cd* Q,
                                         unsigned char* tab, int max_sweeps = 30, bool init_v = true,
                                         double stop_sin2 = 1.0e-16, double skip_abs2 = 0.0,
-                                        long long* prof = nullptr, double act_thr = -INFINITY) {
+                                        long long* prof = nullptr, double act_thr = -INFINITY,
+                                        double skip_loose2 = 0.0) {
   constexpr int B = 16, D2 = 2 * B;
   const int tid = threadIdx.x;
   if (init_v) {
@@ -476,7 +478,7 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
   int sweeps = 0;
   for (; sweeps < max_sweeps; ++sweeps) {
     int rotated = 0;
-    if (sweeps > 0 && act_thr > -INFINITY) {
+    if (act_thr > -INFINITY) {
       if (tid < 16) imp[tid] = 0;
       __syncthreads();
       for (int i = tid; i < d; i += NT)
@@ -504,7 +506,9 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
         if (skip_abs2 > 0.0) {   // (uniform branch; contains the barrier the load needs)
           double t[1] = {off2};
           block_sum<1>(t, reinterpret_cast<double*>(Sb));
-          if (t[0] <= skip_abs2) continue;
+          // block pairs without an entry above act_thr only have to keep the basis a good warm start
+          const bool important = !(act_thr > -INFINITY) || imp[bi] || (bj < nbk && imp[bj]);
+          if (t[0] <= (important ? skip_abs2 : fmax(skip_abs2, skip_loose2))) continue;
         } else {
           __syncthreads();
         }

@@ -231,7 +231,8 @@ __device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const Pl
   const double skip = 1.0e-13 * gm;
   const long long t1 = clock64();
   const int sw = block_jacobi_heig(W, d, V, d, d, sm.S, sm.Sb, sm.Q, sm.tab, 30, false, 1.0e-12, skip * skip,
-                                   tc ? tc + 4 : nullptr, act_thr > -INFINITY ? act_thr - 1.0e-6 * gm : act_thr);
+                                   tc ? tc + 4 : nullptr, act_thr > -INFINITY ? act_thr - 1.0e-6 * gm : act_thr,
+                                   (1.0e-6 * gm) * (1.0e-6 * gm));
   if (tc) { tc[0] += t1 - t0; tc[1] += clock64() - t1; }
   return sw;
 }

@@ -362,3 +362,61 @@ def test_general_complex_A_takes_general_kernel(gpu_ctx):
     snap = {20: None}
     admm.infer_admm(A, B, X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 0.0, 0.0, 20, None, None, admm.argmin_z, None, snap)
     assert rel(Sg[0]["X"], snap[20]["X"]) < 1e-9
+
+
+def _synthetic_case(tx, rx, m, seed, L=3):
+    """2-bit random beams (Generate_random_beam.m:31-34) on a tx x rx array, sparse multipath channel."""
+    from twoace_b200 import harness as hz
+    rng = np.random.default_rng(seed)
+    n = tx * rx
+    _, vecH, _, _ = hz.generate_channel(rng, tx, rx, L)
+    A = np.exp(1j * (np.pi / 2) * rng.integers(0, 4, (m, n))) / np.sqrt(n)
+    B = np.abs(A @ vecH)
+    return A, B, vecH
+
+
+@pytest.mark.parametrize("tx,rx,m", [(4, 4, 24), (8, 8, 40), (8, 4, 30), (32, 32, 96)])
+@pytest.mark.parametrize("nuc", [False, True])
+def test_stage_parity_other_antenna_counts(gpu_ctx, tx, rx, m, nuc):
+    """Rank-shaping profiles other than the 16-antenna one (inferLowRankV4.m:416-443: one stage for 4 and 8
+    antennas, four stages [3 4 6 12] for 32) and n = 1024 (BASELINE config 5 shape) on the general kernel."""
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    A, B, _ = _synthetic_case(tx, rx, m, 17 + tx)
+    A, B, _, _ = admm._preprocess(A, B, 1e-8)
+    n = tx * rx
+    r = min(20, m, n)
+    X0 = admm.spectral_initialize(A, B, r)
+    zfn = admm.argmin_z_nuclear if nuc else admm.argmin_z
+    for iters in (1, 8):
+        snap = {iters: None}
+        tro = admm.StageTrace()
+        admm.infer_admm(A, B, X0, True, False, tx, rx, 0.0, 1e-3, 1.03, 0.0, 0.0, iters, None, None, zfn, tro, snap)
+        p = tw.Params.default(maxiter=iters, tol_rel=0.0, tol_abs=0.0)
+        _, _, Sg, W = sv.infer_admm_batch([A], [B], [X0], True, False, tx, rx, p, nuclear=nuc, ctx=gpu_ctx)
+        assert rel(Sg[0]["X"], snap[iters]["X"]) < 1e-9
+        assert rel(Sg[0]["Y"], snap[iters]["Y"]) < 1e-9
+        assert rel(Sg[0]["Z"], snap[iters]["Z"]) < 1e-9 or np.linalg.norm(snap[iters]["Z"]) < 1e-12
+        assert int(W[0][3]) == tro.opt_iter
+
+
+@pytest.mark.parametrize("tx,rx,m", [(8, 8, 48), (4, 4, 40)])
+def test_full_solve_other_antenna_counts(gpu_ctx, tx, rx, m):
+    """inferLowRankV4 end to end (default tolerances) away from 16 x 16: same flags, quality and CSI."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    from twoace_b200 import solvers as sv
+    A, B, vecH = _synthetic_case(tx, rx, m, 5 + tx)
+    rng = np.random.default_rng(2)
+    tr = sv.draw_train_idx(m, 0.95, 1, rng)
+    info = admm.SolveInfo()
+    Xo, Yo, qo = admm.infer_low_rank_v4(A, B, tx, rx, admm.Params(), train_idx=tr[0], info=info)
+    res = sv.solve_batch(tw.V4, [A], [B], tx, rx, [tr], None, gpu_ctx)
+    rng2 = np.random.default_rng(9)
+    Xs, _, _ = admm.infer_low_rank_v4(A, B * (1 + 1e-14 * rng2.standard_normal(m)), tx, rx, admm.Params(),
+                                      train_idx=tr[0])
+    self_sens = hz.aligned_rel_err(Xs, Xo)
+    assert hz.aligned_rel_err(res.X[0], Xo) < max(1e-6, 100 * self_sens)
+    if self_sens < 1e-6:
+        assert abs(res.quality[0] - qo) < 1e-6
+        assert int(res.info[0][2]) == int(info.used_rank_one) and int(res.info[0][3]) == int(info.rolled_back)

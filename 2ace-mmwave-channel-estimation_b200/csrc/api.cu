@@ -10,6 +10,7 @@
 #include "../../include/twoace.h"
 #include "solve_kernels.cuh"
 #include "phaselift.cuh"
+#include "metrics.cuh"
 
 using namespace twoace;
 
@@ -1090,6 +1091,36 @@ extern "C" int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, c
   }
   rc = host_back(ctx, mem, sig, dSig, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
   rc = host_back(ctx, mem, info, dInfo, (size_t)nb * PL_INFO * sizeof(double)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Evaluation metrics (Evaluation_H.m:81-115)
+extern "C" int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
+                                    const double* X_true, int phase_bit, double* out) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !X_est || !X_true || !out) FAIL(TWOACE_E_INVALID, "null argument");
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  if (tx < 1 || rx < 1 || tx > MET_DMAX || rx > MET_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "metrics: tx, rx must be in 1..%d", MET_DMAX);
+  if (phase_bit < 1 || phase_bit > 8) FAIL(TWOACE_E_INVALID, "phase_bit = %d", phase_bit);
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)tx * rx;
+  Staging st;
+  const void *dE = nullptr, *dT = nullptr;
+  void* dO = nullptr;
+  int rc = dev_in(ctx, st, mem, X_est, (size_t)nb * n * sizeof(cd), &dE); if (rc) return rc;
+  rc = dev_in(ctx, st, mem, X_true, (size_t)nb * n * sizeof(cd), &dT); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, out, (size_t)nb * MET_WORDS * sizeof(double), &dO); if (rc) return rc;
+  const size_t smem = met_smem_bytes();
+  CK(cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  metrics_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, smem, ctx->stream>>>((const cd*)dE, (const cd*)dT, nb, tx, rx,
+                                                                         phase_bit, (double*)dO);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  rc = host_back(ctx, mem, out, dO, (size_t)nb * MET_WORDS * sizeof(double)); if (rc) return rc;
   if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
   return TWOACE_OK;
 }

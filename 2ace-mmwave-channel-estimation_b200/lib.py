@@ -15,6 +15,7 @@ V4, V4_MULTI, NUCLEAR = 0, 1, 2
 INFO_WORDS = 16
 STAGE_WORDS = 16
 PL_INFO_WORDS = 16
+METRIC_WORDS = 4
 
 # every symbol include/twoace.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -23,6 +24,7 @@ EXPORTS = [
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
     "twoace_set_option", "twoace_fast_launch_count", "twoace_pl_default_opts", "twoace_phaselift_batch",
+    "twoace_metrics_batch",
 ]
 
 
@@ -126,6 +128,8 @@ def load() -> C.CDLL:
     lib.twoace_phaselift_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, dp, i32p, C.c_double, dp,
                                            C.POINTER(PlOpts), dp, dp]
     lib.twoace_phaselift_batch.restype = C.c_int
+    lib.twoace_metrics_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]
+    lib.twoace_metrics_batch.restype = C.c_int
     _lib = lib
     return lib
 
@@ -230,6 +234,10 @@ class Context:
     def phaselift_batch_raw(self, mem, nb, n, m, A, cb_rows, row_scale, y, opts, sig, info=None):
         self.check(self.lib.twoace_phaselift_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(cb_rows),
                                                    float(row_scale), _ptr(y), C.byref(opts), _ptr(sig), _ptr(info)))
+
+    def metrics_batch_raw(self, mem, nb, tx, rx, X_est, X_true, phase_bit, out):
+        self.check(self.lib.twoace_metrics_batch(self.h, mem, nb, tx, rx, _ptr(X_est), _ptr(X_true), int(phase_bit),
+                                                 _ptr(out)))
 
     def spectral_init_batch_raw(self, mem, nb, n, m, A, B, r, Xs):
         self.check(self.lib.twoace_spectral_init_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(B), r, _ptr(Xs)))

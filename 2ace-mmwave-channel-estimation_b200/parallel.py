@@ -11,7 +11,8 @@ from __future__ import annotations
 
 import numpy as np
 
-METRICS = ("count", "sum_mse", "n_rank_one", "n_rollback", "sum_quality", "sum_iters")
+METRICS = ("count", "sum_mse", "n_rank_one", "n_rollback", "sum_quality", "sum_iters", "sum_gain_ana", "sum_gain_dig",
+           "sum_proj_err")
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -21,9 +22,11 @@ def shard_range(total: int, rank: int, world: int):
     return lo, hi
 
 
-def local_stats(cell_ids, n_cells: int, mse, info) -> np.ndarray:
+def local_stats(cell_ids, n_cells: int, mse, info, metrics=None) -> np.ndarray:
     """Accumulate per-cell sums for the instances of this rank.
-    cell_ids: int [nb] (e.g. index into the SNR x M grid); mse: [nb]; info: [nb,16] (twoace.h words)."""
+    cell_ids: int [nb] (e.g. index into the SNR x M grid); mse: [nb]; info: [nb,16] (twoace.h words);
+    metrics: optional [nb,4] from twoace_metrics_batch (MSE_H, gain_ana, gain_dig, proj_error), summed over the
+    instances with a finite MSE_H (Evaluation_H.m:81-115; the reference gathers them per trial, Vs_M_par.m:190)."""
     s = np.zeros((n_cells, len(METRICS)), dtype=np.float64)
     cell_ids = np.asarray(cell_ids)
     mse = np.asarray(mse, dtype=np.float64)
@@ -34,6 +37,10 @@ def local_stats(cell_ids, n_cells: int, mse, info) -> np.ndarray:
     np.add.at(s[:, 3], cell_ids, info[:, 3])
     np.add.at(s[:, 4], cell_ids, np.nan_to_num(info[:, 0]))
     np.add.at(s[:, 5], cell_ids, info[:, 15])
+    if metrics is not None:
+        metrics = np.asarray(metrics, dtype=np.float64)
+        for k in range(3):
+            np.add.at(s[:, 6 + k], cell_ids[ok], np.nan_to_num(metrics[ok, 1 + k]))
     return s
 
 

@@ -209,6 +209,19 @@ def phaselift_batch_codebook(rows_list, row_scale: float, y_list, n: int, opts: 
     return [sig[b * n:(b + 1) * n].copy() for b in range(nb)], info
 
 
+def evaluation_batch(X_est, X_true, tx: int, rx: int, phase_bit: int = 2, ctx: _lib.Context | None = None):
+    """Evaluation_H.m:81-115 per instance -> array [nb, 4] = (MSE_H, gain_ana, gain_dig, proj_error).
+    X_est / X_true: [nb, tx*rx] complex (vec of the rx x tx channel, column-major)."""
+    ctx = ctx or _lib.default_context()
+    Xe = np.ascontiguousarray(np.asarray(X_est, np.complex128))
+    Xt = np.ascontiguousarray(np.asarray(X_true, np.complex128))
+    if Xe.shape != Xt.shape or Xe.ndim != 2 or Xe.shape[1] != tx * rx:
+        raise ValueError("X_est and X_true must both be [nb, tx*rx]")
+    out = np.empty((Xe.shape[0], _lib.METRIC_WORDS), np.float64)
+    ctx.metrics_batch_raw(_lib.MEM_HOST, Xe.shape[0], int(tx), int(rx), Xe, Xt, phase_bit, out)
+    return out
+
+
 # ----------------------------------------------------------------------------- MATLAB-signature calls
 def MyPhaseLift(measurements, measurementMat, *, opts: PlOpts | None = None, ctx=None):
     """recoveredSig = MyPhaseLift(measurements, measurementMat)   (MyPhaseLift.m:69)."""

@@ -293,8 +293,14 @@ def ours_arm(args, wl, rank, local_rank, world):
     X = X_d.cpu().numpy().view(np.complex128).reshape(nb, N)
     info = info_d.cpu().numpy().reshape(nb, 16)
     sw = sw_d.cpu().numpy().reshape(nb, nstage, tw.lib.STAGE_WORDS)
-    mse = np.array([hz.nmse(X[b], insts[b].vecH) for b in range(nb)])
-    stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info), dev if world > 1 else None)
+    # evaluation metrics on the device (Evaluation_H.m:81-115): the payload of the reduce
+    Xt_d = torch.from_numpy(np.ascontiguousarray(np.stack([i.vecH for i in insts])).view(np.float64)).to(dev)
+    met_d = torch.empty(nb * tw.lib.METRIC_WORDS, dtype=torch.float64, device=dev)
+    ctx.metrics_batch_raw(tw.lib.MEM_DEVICE, nb, TX, RX, X_d.data_ptr(), Xt_d.data_ptr(), 2, met_d.data_ptr())
+    ctx.synchronize()
+    met = met_d.cpu().numpy().reshape(nb, tw.lib.METRIC_WORDS)
+    mse = met[:, 0]
+    stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info, met), dev if world > 1 else None)
 
     # ---- roofline of the dominant kernel (admm_stage_kernel), live CUDA-event durations
     flops_step = solve_flops(insts, sw, wl["variant"])
@@ -361,6 +367,8 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "nmse_delta_db": nmse_delta,
                 "nmse_db_per_cell": [None if not np.isfinite(v) else float(v) for v in par.nmse_db_per_cell(stats)],
+                "metrics_mean": {k: float(stats[:, 6 + j].sum() / max(stats[:, 0].sum(), 1.0))
+                                 for j, k in enumerate(("gain_ana", "gain_dig", "proj_error"))},
                 "e2e_vs_device_max_abs_diff": e2e_match}
         print(json.dumps(line), flush=True)
 

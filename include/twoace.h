@@ -169,6 +169,15 @@ int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_
                            const int32_t* cb_rows, double row_scale, const double* y,
                            const twoace_pl_opts* opts, double* sig, double* info);
 
+/* ---- Evaluation metrics ---------------------------------------------------------------
+ * Per instance, Evaluation_H.m:81-115: out[b*4 + {0,1,2,3}] = MSE_H, gain_ana, gain_dig, proj_error of the
+ * recovered channel X_est[b] against the ground truth X_true[b] (vec of the rx x tx channel matrix, column-major,
+ * tx, rx <= 32).  Singular pairs are phase-normalised canonically (largest-modulus entry of v real positive);
+ * a NaN or all-zero estimate yields NaN metrics. */
+#define TWOACE_METRIC_WORDS 4
+int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
+                         const double* X_true, int phase_bit, double* out);
+
 /* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
  * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
  * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass. */

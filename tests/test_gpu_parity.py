@@ -420,3 +420,31 @@ def test_full_solve_other_antenna_counts(gpu_ctx, tx, rx, m):
     if self_sens < 1e-6:
         assert abs(res.quality[0] - qo) < 1e-6
         assert int(res.info[0][2]) == int(info.used_rank_one) and int(res.info[0][3]) == int(info.rolled_back)
+
+
+@pytest.mark.parametrize("tx,rx", [(16, 16), (8, 4), (32, 32)])
+def test_evaluation_metrics_parity(gpu_ctx, tx, rx):
+    """twoace_metrics_batch against oracle/metrics.py (Evaluation_H.m:81-115): MSE_H, gain_ana, gain_dig,
+    proj_error to 1e-9 relative; NaN estimates give NaN."""
+    from oracle import metrics as om
+    from twoace_b200 import harness as hz
+    from twoace_b200 import solvers as sv
+    rng = np.random.default_rng(40 + tx)
+    n = tx * rx
+    Xt, Xe = [], []
+    for k in range(12):
+        _, vecH, _, _ = hz.generate_channel(rng, tx, rx, 3)
+        noise = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (0.02 * (k + 1))
+        Xt.append(vecH)
+        Xe.append((vecH + noise) * np.exp(1j * rng.uniform(0, 6.28)) * rng.uniform(0.5, 2.0))
+    Xe[5] = Xe[5].copy()
+    Xe[5][0] = np.nan
+    Xe[7] = np.zeros(n, complex)
+    got = sv.evaluation_batch(np.array(Xe), np.array(Xt), tx, rx, 2, gpu_ctx)
+    for k in range(12):
+        ref = om.evaluation_h(Xe[k], Xt[k], tx, rx, 2)
+        if k in (5, 7):
+            assert np.all(np.isnan(got[k])) and all(np.isnan(v) for v in ref)
+            continue
+        for j in range(4):
+            assert abs(got[k, j] - ref[j]) <= 1e-9 * max(abs(ref[j]), 1e-3), (k, j, got[k], ref)

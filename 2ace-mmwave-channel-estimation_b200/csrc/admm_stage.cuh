@@ -188,9 +188,15 @@ __device__ inline int rank_profile_dev(int tx, int rx, int m, int n, int rank_on
   const double sq = sqrt((double)sz);
   const int r0 = (int)ceil(sq * 0.5), r1 = (int)ceil(sq * 0.7), r2 = (int)ceil(sq);
   const int r3 = min(sz, (int)ceil(sq * 2.0));
-  if (rank_one) { rl[0] = 1; fl[0] = 0.95; return 1; }
+  // rank_one also carries the profile of the older solver versions: 2 = inferLowRank.m:407-418,437 (single
+  // stage [r2]), 3 = inferLowRankV2.m:418-431 (small-array fallback [r2 r3] instead of [r2])
+  if (rank_one == 1) { rl[0] = 1; fl[0] = 0.95; return 1; }
+  if (rank_one == 2) { rl[0] = min(sz, r2); fl[0] = 0.95; return 1; }
   if ((long long)m >= (long long)n * 3) { rl[0] = r3; fl[0] = 0.995; return 1; }
-  if (r1 <= 2) { rl[0] = r2; fl[0] = 0.95; return 1; }
+  if (r1 <= 2) {
+    if (rank_one == 3) { rl[0] = r2; rl[1] = r3; fl[0] = 0.95; fl[1] = 0.995; return 2; }
+    rl[0] = r2; fl[0] = 0.95; return 1;
+  }
   if (r0 <= 2) { rl[0] = r1; rl[1] = r2; rl[2] = r3; fl[0] = 0.9; fl[1] = 0.95; fl[2] = 0.995; return 3; }
   rl[0] = r0; rl[1] = r1; rl[2] = r2; rl[3] = r3;
   fl[0] = 0.8; fl[1] = 0.9; fl[2] = 0.95; fl[3] = 0.995;

@@ -204,7 +204,8 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
 
 static bool fast_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
   return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
-         t.m <= 256 && (t.r == 20 || t.r == 1) && (!t.nuclear || t.r == 1 || t.m >= 26);
+         t.m <= 256 && (t.r == 20 || t.r == 1) && (!t.nuclear || t.r == 1 || t.m >= 26) &&
+         (t.rank_one == 0 || t.rank_one == 1);   // (the profiles of inferLowRank.m / V2.m: general kernel)
 }
 
 static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
@@ -395,6 +396,12 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   const int nuclear = in.variant == TWOACE_NUCLEAR ? 1 : 0;
   const int T = multi ? 3 : 1;
   const int nstage = 4 * T + 1;
+  // older solver versions (ADMM_v2.m:26-31): no rank-one rerun; V1 / V2 refine only when quality > 0.6; their
+  // rank profile travels in StageTask.rank_one (2: inferLowRank.m, 3: inferLowRankV2.m -- identical to the V4
+  // profile once ceil(0.7 sqrt(min(tx,rx))) > 2, i.e. from 9 antennas on)
+  const bool older = in.variant == TWOACE_V3 || in.variant == TWOACE_V2 || in.variant == TWOACE_V1;
+  const int refine_if_good = (in.variant == TWOACE_V2 || in.variant == TWOACE_V1) ? 1 : 0;
+  const int prof = in.variant == TWOACE_V1 ? 2 : (in.variant == TWOACE_V2 && std::min(in.tx, in.rx) < 9) ? 3 : 0;
   const bool dense = in.dA != nullptr;
 
   // ---- host bookkeeping (integer index work is bit-exact host code)
@@ -574,7 +581,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.B = in.dB + b_off[b]; a.brows = d_trainB + tr_off[b] + (size_t)t * mtr[b];
         a.bscale = &d_ctl[b].b_scale; a.m = mtr[b]; a.r = rb[b];
         a.X0 = d_Xs + (size_t)b * xstride; a.Xout = d_Xa + (size_t)b * xstride; a.Yout = nullptr;
-        a.sbr = 1; a.rank_one = pass; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
+        a.sbr = 1; a.rank_one = pass ? 1 : prof; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
         a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
         a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
@@ -592,13 +599,16 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         q.bscale = &d_ctl[b].b_scale; q.mte = mte[b]; q.x = d_xb + (size_t)b * n; q.y = d_yb + b_off[b];
         q.mtr = mtr[b]; q.xmax = d_xmax + (size_t)b * n; q.ymax = d_ymax + b_off[b];
         q.ctl = d_ctl + b; q.trial = t; q.pass = pass; q.multi = multi ? 1 : 0;
+        q.allow_r1 = older ? 0 : 1; q.refine_if_good = refine_if_good;
       }
-      rc = launch_stage(ctx, sa, prm, n, in.tx, in.rx, cursor);
-      if (rc) return rc;
-      rc = launch_ortho(ctx, ot, n, cursor);
-      if (rc) return rc;
-      rc = launch_stage(ctx, sb, prm, n, in.tx, in.rx, cursor);
-      if (rc) return rc;
+      if (!(pass == 1 && older)) {   // (older versions have no rank-one rerun; pass 1 only does the bookkeeping)
+        rc = launch_stage(ctx, sa, prm, n, in.tx, in.rx, cursor);
+        if (rc) return rc;
+        rc = launch_ortho(ctx, ot, n, cursor);
+        if (rc) return rc;
+        rc = launch_stage(ctx, sb, prm, n, in.tx, in.rx, cursor);
+        if (rc) return rc;
+      }
       const QualTask* dq = nullptr;
       rc = upload_tasks(ctx, qt, cursor, &dq);
       if (rc) return rc;
@@ -616,15 +626,15 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.A = aview(b, dense ? nullptr : d_fullA + b_off[b]);
       a.B = in.dB + b_off[b]; a.brows = nullptr; a.bscale = &d_ctl[b].b_scale;
       a.m = in.m[b]; a.r = 1; a.X0 = d_xmax + (size_t)b * n; a.Xout = d_xr + (size_t)b * n; a.Yout = d_yr + b_off[b];
-      a.sbr = 1; a.rank_one = 0; a.nuclear = nuclear; a.rank_one_ptr = &d_ctl[b].use_rank_one;
-      a.active = nullptr; a.active_expect = 1;
+      a.sbr = 1; a.rank_one = prof; a.nuclear = nuclear; a.rank_one_ptr = older ? nullptr : &d_ctl[b].use_rank_one;
+      a.active = refine_if_good ? &d_ctl[b].refine_on : nullptr; a.active_expect = 1;
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
       a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
       a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
       FinalTask& f = ft[b];
       f.x0 = d_xmax + (size_t)b * n; f.y0 = d_ymax + b_off[b]; f.xr = d_xr + (size_t)b * n; f.yr = d_yr + b_off[b];
       f.m = in.m[b]; f.mtr = mtr[b]; f.Xout = in.dX + (size_t)b * n; f.Yout = in.dY + b_off[b];
-      f.quality_out = in.dQ + b; f.ctl = d_ctl + b;
+      f.quality_out = in.dQ + b; f.ctl = d_ctl + b; f.refine_if_good = refine_if_good;
     }
     rc = launch_stage(ctx, sr, prm, n, in.tx, in.rx, cursor);
     if (rc) return rc;
@@ -681,7 +691,7 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
                         double* quality, double* info, double* stage_words) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
-  if (variant < TWOACE_V4 || variant > TWOACE_NUCLEAR) FAIL(TWOACE_E_INVALID, "unknown variant %d", variant);
+  if (variant < TWOACE_V4 || variant > TWOACE_V1) FAIL(TWOACE_E_INVALID, "unknown variant %d", variant);
   if (nb < 0 || !m || !B || !train_idx || !X || !Y || !quality) FAIL(TWOACE_E_INVALID, "null argument");
   if (!A && !cb_rows) FAIL(TWOACE_E_INVALID, "neither dense A nor codebook rows given");
   if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");

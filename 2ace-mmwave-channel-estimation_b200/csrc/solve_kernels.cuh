@@ -26,6 +26,7 @@ struct InstCtl {
   double trial_quality[3];
   double c_scale;      // quantised codebooks: A_eff = c_scale * u(code)
   int quant;           // 1 when every entry of A is c * {1, j, -1, -j}
+  int refine_on;       // 0 when the refine stage is skipped (inferLowRankV2.m:47: only if quality > 0.6)
 };
 
 // ---- pre-processing ----------------------------------------------------------------------
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(NT) prep_kernel(const PrepTask* __restrict__ t
       c.out_scale = B_norm / A_norm;
       c.quality = NAN; c.max_quality = -1.0; c.similarity = NAN;
       c.need_r1 = 0; c.use_rank_one = 0; c.best_trial = -1; c.rolled_back = 0; c.y_rows = m;
+      c.refine_on = 1;
       c.trial_r1_mask = 0;
       c.trial_quality[0] = c.trial_quality[1] = c.trial_quality[2] = NAN;
       c.c_scale = c.a_scale * tk.code_mag;
@@ -340,6 +342,8 @@ struct QualTask {
   int trial;
   int pass;            // 0: after the first impl run; 1: after the (masked) rank-one rerun
   int multi;           // 1: keep the best of the trials; 0: always take the current trial
+  int allow_r1;        // 0: no rank-one rerun (inferLowRankV3.m and older)
+  int refine_if_good;  // 1: the refine stage only runs when quality > 0.6 (inferLowRankV2.m:47, inferLowRank.m:47)
 };
 
 __global__ void __launch_bounds__(NT) quality_kernel(const QualTask* __restrict__ tasks, int ntasks, int n) {
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(NT) quality_kernel(const QualTask* __restrict_
         const double q = 1.0 - sqrt(v[0]) / sqrt(v[1]);
         ctl->quality = q;
         if (tk.pass == 0) {
-          const int nr1 = (q < 0.6) ? 1 : 0;     // NaN -> no rerun, like MATLAB's comparison
+          const int nr1 = (tk.allow_r1 && q < 0.6) ? 1 : 0;     // NaN -> no rerun, like MATLAB's comparison
           ctl->need_r1 = nr1;
           ctl->use_rank_one = nr1;
           if (nr1) ctl->trial_r1_mask |= (1 << tk.trial);
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(NT) quality_kernel(const QualTask* __restrict_
         int take = tk.multi ? (ctl->max_quality < q) : 1;
         if (take) { ctl->max_quality = q; ctl->best_trial = tk.trial; }
         ctl->need_r1 = 0;
+        ctl->refine_on = (tk.refine_if_good && !(q > 0.6)) ? 0 : 1;
         s_take = take;
       }
       __syncthreads();
@@ -408,6 +413,7 @@ struct FinalTask {
   cd* Xout; cd* Yout;           // n, m
   double* quality_out;
   InstCtl* ctl;
+  int refine_if_good;           // see QualTask
 };
 
 __global__ void __launch_bounds__(NT) final_kernel(const FinalTask* __restrict__ tasks, int ntasks, int n) {
@@ -425,15 +431,16 @@ __global__ void __launch_bounds__(NT) final_kernel(const FinalTask* __restrict__
     block_sum<4>(v, red);
     const double q = ctl->quality;
     const double sim = sqrt(v[0] * v[0] + v[1] * v[1]) / sqrt(v[2]) / sqrt(v[3]);
-    const bool rollback = (q > 0.6) && (sim < 0.6);
+    const bool norefine = tk.refine_if_good && !(q > 0.6);   // the refine stage did not run: keep the train solution
+    const bool rollback = !norefine && (q > 0.6) && (sim < 0.6);
     const double os = ctl->out_scale;
-    const cd* xs = rollback ? tk.x0 : tk.xr;
-    const cd* ys = rollback ? tk.y0 : tk.yr;
-    const int yr = rollback ? tk.mtr : tk.m;
+    const cd* xs = (rollback || norefine) ? tk.x0 : tk.xr;
+    const cd* ys = (rollback || norefine) ? tk.y0 : tk.yr;
+    const int yr = (rollback || norefine) ? tk.mtr : tk.m;
     for (int k = tid; k < n; k += NT) tk.Xout[k] = cscale(xs[k], os);
     for (int i = tid; i < tk.m; i += NT) tk.Yout[i] = (i < yr) ? cscale(ys[i], os) : cmk(0.0, 0.0);
     if (tid == 0) {
-      if (q > 0.6) ctl->similarity = sim;
+      if (q > 0.6 && !norefine) ctl->similarity = sim;
       ctl->rolled_back = rollback ? 1 : 0;
       ctl->y_rows = yr;
       *tk.quality_out = q;

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import lib as _lib
-from .lib import NUCLEAR, V4, V4_MULTI, Params, PlOpts
+from .lib import NUCLEAR, V1, V2, V3, V4, V4_MULTI, Params, PlOpts
 
 __all__ = ["inferLowRankV4", "inferLowRankV4_multi", "inferLowRank_Nuclear", "ADMM_v2", "ADMM_v2_nuclear",
            "solve_batch", "solve_batch_codebook", "infer_admm_batch", "spectral_init_batch", "BatchResult",
@@ -261,13 +261,38 @@ def inferLowRank_Nuclear(A, B, tx, rx, lambda_=0.0, r=20, mu0=1e-3, rho=1.03, cc
                    train_idx, rng, ctx)
 
 
+def inferLowRankV3(A, B, tx, rx, lambda_=0.0, r=20, mu0=1e-3, rho=1.03, cc_frac=0.95, tol_rel=1e-4,
+                   tol_abs=1e-8, maxiter=500, *, train_idx=None, rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRankV3(...): V4 without the rank-one rerun (inferLowRankV3.m:1)."""
+    return _single(V3, A, B, tx, rx, _params(lambda_, r, mu0, rho, cc_frac, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
+def inferLowRankV2(A, B, tx, rx, lambda_=0.0, r=20, tol_rel=1e-4, tol_abs=1e-8, maxiter=500, *, train_idx=None,
+                   rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRankV2(A, B, tx, rx, lambda, r, tol_rel, tol_abs, maxiter)  (inferLowRankV2.m:1;
+    mu0 = 1e-3, rho = 1.03 and the 95 % split are hard-coded there)."""
+    return _single(V2, A, B, tx, rx, _params(lambda_, r, 1e-3, 1.03, 0.95, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
+def inferLowRank(A, B, tx, rx, lambda_=0.0, r=20, tol_rel=1e-4, tol_abs=1e-8, maxiter=500, *, train_idx=None,
+                 rng=None, ctx=None):
+    """[X, Y, quality] = inferLowRank(A, B, tx, rx, lambda, r, tol_rel, tol_abs, maxiter)  (inferLowRank.m:1)."""
+    return _single(V1, A, B, tx, rx, _params(lambda_, r, 1e-3, 1.03, 0.95, tol_rel, tol_abs, maxiter),
+                   train_idx, rng, ctx)
+
+
 def ADMM_v2(measurements, FW, TX, RX, version, *, tree="main", train_idx=None, rng=None, ctx=None):
     """[X, Y, converged] = ADMM_v2(measurements, FW, TX, RX, version).  As in the reference the third
-    output is really ``quality`` (ADMM_v2.m:31-32 vs inferLowRankV4.m:1).  Versions outside the
-    V4 family (SURVEY.md §2.2 rows 0-3 of ``main``) are not part of this build."""
+    output is really ``quality`` (ADMM_v2.m:31-32 vs inferLowRankV4.m:1).  Version 0 (inferMinL2) and the
+    version >= 5 loop (which passes lambda != 0) are not part of this build."""
     B = np.asarray(measurements, dtype=np.float64).reshape(-1)
     if tree == "main" and version == 4:
         return inferLowRankV4_multi(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
+    if tree == "main" and version in (1, 2, 3):                                         # ADMM_v2.m:26-31
+        fn = {1: inferLowRank, 2: inferLowRankV2, 3: inferLowRankV3}[version]
+        return fn(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
     if tree == "ns" and version == 3:
         return inferLowRankV4(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
     raise NotImplementedError(f"ADMM_v2 version {version} (tree {tree!r}) is outside the accelerated hot path")

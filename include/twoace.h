@@ -45,7 +45,10 @@ enum { TWOACE_MEM_HOST = 0, TWOACE_MEM_DEVICE = 1 };
 enum {
   TWOACE_V4 = 0,        /* inferLowRankV4.m        (NS ADMM_v2.m version 3)        */
   TWOACE_V4_MULTI = 1,  /* inferLowRankV4_multi.m  (main ADMM_v2.m version 4)       */
-  TWOACE_NUCLEAR = 2    /* inferLowRank_Nuclear.m  (main ADMM_v2_nuclear.m version 4) */
+  TWOACE_NUCLEAR = 2,   /* inferLowRank_Nuclear.m  (main ADMM_v2_nuclear.m version 4) */
+  TWOACE_V3 = 3,        /* inferLowRankV3.m        (main ADMM_v2.m version 3): V4 without the rank-one rerun */
+  TWOACE_V2 = 4,        /* inferLowRankV2.m        (main ADMM_v2.m version 2): refine only if quality > 0.6  */
+  TWOACE_V1 = 5         /* inferLowRank.m          (main ADMM_v2.m version 1): single-stage rank profile     */
 };
 
 /* Optional positional arguments of inferLowRankV4.m:2-9 (defaults in twoace_default_params). */

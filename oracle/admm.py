@@ -131,18 +131,23 @@ def argmin_x(A, Y, Z, M, N, mu, lam, U, D):
 
 # inferLowRankV4.m:416-443
 def rank_profile(tx, rx, m, n, use_rank_one):
+    """inferLowRankV4.m:416-443.  ``use_rank_one``: False/True as in V4, or the profile code of an older
+    version: 2 = inferLowRank.m:407-418,437 (single stage [r2]), 3 = inferLowRankV2.m:418-431 (as V3/V4 except
+    the small-array fallback [r2 r3])."""
     sz = min(rx, tx)
     r0 = math.ceil(math.sqrt(sz) * 0.5)
     r1 = math.ceil(math.sqrt(sz) * 0.7)
     r2 = math.ceil(math.sqrt(sz))
     r3 = min(sz, math.ceil(math.sqrt(sz) * 2.0))
     f0, f1, f2, f3 = 0.8, 0.9, 0.95, 0.995
-    if use_rank_one:
+    if use_rank_one == 1:
         return [1], [0.95]
+    if use_rank_one == 2:
+        return [min(tx, rx, r2)], [f2]
     if m >= n * 3:
         return [r3], [f3]
     if r1 <= 2:
-        return [r2], [f2]
+        return ([r2, r3], [f2, f3]) if use_rank_one == 3 else ([r2], [f2])
     if r0 <= 2:
         return [r1, r2, r3], [f1, f2, f3]
     return [r0, r1, r2, r3], [f0, f1, f2, f3]
@@ -446,6 +451,43 @@ def _v4_like(A, B, tx, rx, p: Params, train_idx, argmin_z_fn, info: SolveInfo):
     return X.reshape(-1) * s, Y.reshape(-1) * s, quality
 
 
+def _older_version(A, B, tx, rx, p: Params, train_idx, info: SolveInfo, profile: int, refine_only_if_good: bool):
+    """inferLowRankV3.m:1-70 / inferLowRankV2.m:1-66 / inferLowRank.m:1-66: the V4 flow without the rank-one
+    retry; V1 / V2 skip the refine when quality <= 0.6 (V2.m:47-58), V3 refines either way (V3.m:50-62)."""
+    A = np.asarray(A, dtype=np.complex128)
+    m, n = A.shape
+    r = min(p.r, m, n)
+    A, B, A_norm, B_norm = _preprocess(A, B, p.tol_abs)
+    train_idx = np.asarray(train_idx, dtype=np.int64)
+    test_idx = test_index_set(m, train_idx)
+    A_train, B_train = A[train_idx, :], B[train_idx]
+    Xs = spectral_initialize(A_train, B_train, r)            # V3.m:213-224 (inside inferLowRankImpl there)
+    X, Y, _ = infer_low_rank_impl(A_train, B_train, Xs, tx, rx, p.lam, r, p.mu0, p.rho, p.tol_rel, p.tol_abs,
+                                  p.maxiter, profile, argmin_z, info.traces)
+    quality = quality_score(A[test_idx, :], B[test_idx], X)
+    info.quality, info.used_rank_one = quality, False
+    info.trial_quality, info.trial_rank_one = [quality], [False]
+    if quality > 0.6 or not refine_only_if_good:
+        X, Y = _refine(A, B, X, Y, quality, profile, tx, rx, p, argmin_z, info)
+    s = B_norm / A_norm
+    return X.reshape(-1) * s, Y.reshape(-1) * s, quality
+
+
+def infer_low_rank_v3(A, B, tx, rx, params: Params | None = None, *, train_idx, info: SolveInfo | None = None):
+    """inferLowRankV3.m (main ADMM_v2.m version 3)."""
+    return _older_version(A, B, tx, rx, params or Params(), train_idx, info or SolveInfo(), 0, False)
+
+
+def infer_low_rank_v2(A, B, tx, rx, params: Params | None = None, *, train_idx, info: SolveInfo | None = None):
+    """inferLowRankV2.m (main ADMM_v2.m version 2; mu0 = 1e-3, rho = 1.03, 95 % split are hard-coded there)."""
+    return _older_version(A, B, tx, rx, params or Params(), train_idx, info or SolveInfo(), 3, True)
+
+
+def infer_low_rank_v1(A, B, tx, rx, params: Params | None = None, *, train_idx, info: SolveInfo | None = None):
+    """inferLowRank.m (main ADMM_v2.m version 1)."""
+    return _older_version(A, B, tx, rx, params or Params(), train_idx, info or SolveInfo(), 2, True)
+
+
 def infer_low_rank_v4(A, B, tx, rx, params: Params | None = None, *, train_idx, info: SolveInfo | None = None):
     """inferLowRankV4.m:1-88.  ``train_idx``: the randsample draw of :37 (0-based, drawn order)."""
     return _v4_like(A, B, tx, rx, params or Params(), train_idx, argmin_z, info or SolveInfo())
@@ -498,6 +540,9 @@ def admm_v2(measurements, FW, TX, RX, version, *, train_idx, tree="main", params
     B = np.asarray(measurements, dtype=np.float64).reshape(-1)
     if tree == "main" and version == 4:
         return infer_low_rank_v4_multi(FW, B, TX, RX, params, train_idx=train_idx, info=info)
+    if tree == "main" and version in (1, 2, 3):
+        fn = {1: infer_low_rank_v1, 2: infer_low_rank_v2, 3: infer_low_rank_v3}[version]
+        return fn(FW, B, TX, RX, params, train_idx=train_idx, info=info)
     if tree == "main_nuclear" and version == 4:
         return infer_low_rank_nuclear(FW, B, TX, RX, params, train_idx=train_idx, info=info)
     if tree == "ns" and version == 3:

@@ -448,3 +448,54 @@ def test_evaluation_metrics_parity(gpu_ctx, tx, rx):
             continue
         for j in range(4):
             assert abs(got[k, j] - ref[j]) <= 1e-9 * max(abs(ref[j]), 1e-3), (k, j, got[k], ref)
+
+
+@pytest.mark.parametrize("version", [1, 2, 3])
+@pytest.mark.parametrize("case", ["cb16_M64", "cb16_M36", "syn8x8", "syn4x4_bad"])
+def test_older_solver_versions_parity(codebook, gpu_ctx, version, case):
+    """inferLowRank.m / inferLowRankV2.m / inferLowRankV3.m (main ADMM_v2.m versions 1-3) through ADMM_v2:
+    V1 runs the general kernel (its single-stage rank profile), V2 / V3 the shared-memory kernel on 16 x 16.
+    Same bar as the V4 full solves: reference-determined instances within 1e-6, quality and Y length equal."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    from twoace_b200 import solvers as sv
+    rng = np.random.default_rng(77)
+    if case.startswith("cb16"):
+        M = int(case.split("M")[1])
+        ins = hz.make_batch(2, codebook, M, 20.0)[1]
+        A, B, tx, rx = ins.A, ins.B, 16, 16
+    elif case == "syn8x8":
+        A, B, _ = _synthetic_case(8, 8, 48, 3)
+        tx = rx = 8
+    else:
+        A, B, _ = _synthetic_case(4, 4, 40, 4)
+        tx = rx = 4
+    m = A.shape[0]
+    tr = sv.draw_train_idx(m, 0.95, 1, rng)
+    if case == "syn4x4_bad":
+        # consistent training rows, held-out rows off by 10x: quality ~ 0.1 <= 0.6 whatever the solver finds
+        # (V1 / V2 then skip the refine, V3 refines without the roll-back test)
+        test_rows = np.setdiff1d(np.arange(m), tr[0])
+        B = B.copy()
+        B[test_rows] *= 10.0
+    fn = {1: admm.infer_low_rank_v1, 2: admm.infer_low_rank_v2, 3: admm.infer_low_rank_v3}[version]
+    info = admm.SolveInfo()
+    Xo, Yo, qo = fn(A, B, tx, rx, admm.Params(), train_idx=tr[0], info=info)
+    rng2 = np.random.default_rng(9)
+    Xs, _, _ = fn(A, B * (1 + 1e-14 * rng2.standard_normal(m)), tx, rx, admm.Params(), train_idx=tr[0])
+    self_sens = hz.aligned_rel_err(Xs, Xo)
+    f0 = gpu_ctx.fast_launch_count
+    Xg, Yg, qg = sv.ADMM_v2(B, A, tx, rx, version, train_idx=tr, ctx=gpu_ctx)
+    used_fast = gpu_ctx.fast_launch_count > f0
+    assert used_fast == (case.startswith("cb16") and version != 1)
+    if case != "syn4x4_bad" or self_sens < 1e-6:
+        # (inconsistent data is decided by rounding noise in the reference itself, heavy-tailed: the 'bad' case
+        #  only checks the control flow below unless the oracle reproduces itself)
+        assert hz.aligned_rel_err(Xg, Xo) < max(1e-6, 100 * self_sens)
+    if self_sens < 1e-6:
+        assert abs(qg - qo) < 1e-6
+    if case == "syn4x4_bad":
+        assert not qo > 0.6
+        res = sv.solve_batch({1: tw.V1, 2: tw.V2, 3: tw.V3}[version], [A], [B], tx, rx, [tr], None, gpu_ctx)
+        assert int(res.info[0][5]) == len(Yo) == (m if version == 3 else len(tr[0]))
+        assert int(res.info[0][3]) == 0          # not a roll-back

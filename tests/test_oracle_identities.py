@@ -166,3 +166,34 @@ def test_fixed_iteration_mode_runs_exactly_maxiter():
     tr = admm.StageTrace()
     admm.infer_admm(A, B, X0, True, False, 4, 4, 0.0, 1e-3, 1.03, 0.0, 0.0, 37, trace=tr)
     assert tr.iters == 37 and not tr.converged
+
+
+def test_older_version_profiles_and_flow():
+    """inferLowRank.m / inferLowRankV2.m / inferLowRankV3.m (ADMM_v2.m:26-31) as deltas of the V4 flow."""
+    from oracle import admm
+    # rank profiles: V1 single stage [r2]; V2 differs from V3/V4 only in the small-array fallback
+    assert admm.rank_profile(16, 16, 60, 256, 2) == ([4], [0.95])
+    assert admm.rank_profile(16, 16, 60, 256, 3) == admm.rank_profile(16, 16, 60, 256, False)
+    assert admm.rank_profile(8, 8, 40, 64, 3) == ([3, 6], [0.95, 0.995])
+    assert admm.rank_profile(8, 8, 40, 64, False) == ([3], [0.95])
+    assert admm.rank_profile(4, 4, 100, 16, 2) == ([2], [0.95])          # m >= 3n does not matter for V1
+    rng = np.random.default_rng(8)
+    n, m = 16, 40
+    A = np.exp(1j * (np.pi / 2) * rng.integers(0, 4, (m, n))) / 4
+    h = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    B = np.abs(A @ h)
+    tr = rng.permutation(m)[:38]
+    p = admm.Params(maxiter=60)
+    i3, i4 = admm.SolveInfo(), admm.SolveInfo()
+    X3, Y3, q3 = admm.infer_low_rank_v3(A, B, 4, 4, p, train_idx=tr, info=i3)
+    X4, Y4, q4 = admm.infer_low_rank_v4(A, B, 4, 4, p, train_idx=tr, info=i4)
+    if not i4.used_rank_one:                                             # no rerun: V3 and V4 coincide exactly
+        assert np.array_equal(X3, X4) and q3 == q4
+    # V2 with a useless measurement set: quality <= 0.6 -> no refine, Y keeps the m_train rows
+    Bbad = rng.uniform(0.1, 1.0, m)
+    i2 = admm.SolveInfo()
+    X2, Y2, q2 = admm.infer_low_rank_v2(A, Bbad, 4, 4, p, train_idx=tr, info=i2)
+    X3b, Y3b, q3b = admm.infer_low_rank_v3(A, Bbad, 4, 4, p, train_idx=tr)
+    assert q2 == q3b
+    if not q2 > 0.6:
+        assert Y2.shape == (38,) and Y3b.shape == (m,)

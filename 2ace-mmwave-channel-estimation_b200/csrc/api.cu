@@ -33,6 +33,7 @@ struct twoace_ctx {
   double cb_mag = 0.0;
   int opt_fast = 1;      // 1: use the shared-memory cluster kernel when a launch is eligible
   int opt_fast_cs = 2;   // cluster size for the r = 20 stages (2 or 4)
+  int opt_dedup_nuclear = 0;   // 1: do not re-execute the (bit-identical) rank-one rerun of inferLowRank_Nuclear
   int64_t fast_launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
@@ -601,7 +602,11 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         q.ctl = d_ctl + b; q.trial = t; q.pass = pass; q.multi = multi ? 1 : 0;
         q.allow_r1 = older ? 0 : 1; q.refine_if_good = refine_if_good;
       }
-      if (!(pass == 1 && older)) {   // (older versions have no rank-one rerun; pass 1 only does the bookkeeping)
+      // Older versions have no rank-one rerun; pass 1 only does the bookkeeping.  inferLowRank_Nuclear.m:69-70
+      // reruns inferLowRankImpl with use_rank_one = true, but its ArgMinZ (:411-419) ignores that flag, so the
+      // rerun recomputes the first run bit for bit; with the opt-in "dedup_nuclear_rerun" it is not re-executed
+      // (same X, Y, quality and flags; the stage words of the elided stages stay zero).
+      if (!(pass == 1 && (older || (nuclear && ctx->opt_dedup_nuclear)))) {
         rc = launch_stage(ctx, sa, prm, n, in.tx, in.rx, cursor);
         if (rc) return rc;
         rc = launch_ortho(ctx, ot, n, cursor);
@@ -1207,6 +1212,7 @@ extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   if (k == "fast") ctx->opt_fast = value ? 1 : 0;
   else if (k == "fast_cs") { if (value != 2 && value != 4) FAIL(TWOACE_E_INVALID, "fast_cs must be 2 or 4"); ctx->opt_fast_cs = value; }
   else if (k == "chunk") { if (value < 1) FAIL(TWOACE_E_INVALID, "chunk must be >= 1"); ctx->chunk = value; }
+  else if (k == "dedup_nuclear_rerun") ctx->opt_dedup_nuclear = value ? 1 : 0;
   else FAIL(TWOACE_E_INVALID, "unknown option %s", key);
   return TWOACE_OK;
 }

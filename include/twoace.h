@@ -183,7 +183,10 @@ int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const
 
 /* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
  * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
- * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass. */
+ * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass;
+ * "dedup_nuclear_rerun" (default 0): inferLowRank_Nuclear.m:69-70 reruns the train solve with use_rank_one = true,
+ * a flag its ArgMinZ (:411-419) never reads, so the rerun reproduces the first run bit for bit; 1 = do not
+ * re-execute it (identical X, Y, quality, flags; roughly 1.6x fewer iterations when quality < 0.6). */
 int twoace_set_option(twoace_ctx* ctx, const char* key, int value);
 /* InferADMM launches that took the shared-memory cluster kernel since context creation. */
 int64_t twoace_fast_launch_count(const twoace_ctx* ctx);

@@ -499,3 +499,26 @@ def test_older_solver_versions_parity(codebook, gpu_ctx, version, case):
         res = sv.solve_batch({1: tw.V1, 2: tw.V2, 3: tw.V3}[version], [A], [B], tx, rx, [tr], None, gpu_ctx)
         assert int(res.info[0][5]) == len(Yo) == (m if version == 3 else len(tr[0]))
         assert int(res.info[0][3]) == 0          # not a roll-back
+
+
+def test_nuclear_rerun_dedup_is_bitwise_identical(codebook, gpu_ctx):
+    """inferLowRank_Nuclear.m:69-70 reruns the train solve with use_rank_one = true, which its ArgMinZ never
+    reads: the opt-in "dedup_nuclear_rerun" must return exactly what the literal flow returns."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    from twoace_b200 import solvers as sv
+    insts = hz.make_batch(3, codebook, 32, 0.0) + hz.make_batch(2, codebook, 64, 10.0)
+    p = tw.Params.default(maxiter=120).fixed_iters()
+    args = ([i.A for i in insts], [i.B for i in insts], 16, 16, [i.train_idx[:1] for i in insts], p, gpu_ctx)
+    lit = sv.solve_batch(tw.NUCLEAR, *args)
+    gpu_ctx.set_option("dedup_nuclear_rerun", 1)
+    try:
+        ded = sv.solve_batch(tw.NUCLEAR, *args)
+    finally:
+        gpu_ctx.set_option("dedup_nuclear_rerun", 0)
+    assert lit.info[:, 2].sum() > 0                      # the rerun really fired somewhere
+    assert np.array_equal(lit.X, ded.X) and np.array_equal(lit.quality, ded.quality)
+    for a, b in zip(lit.Y, ded.Y):
+        assert np.array_equal(a, b)
+    assert np.array_equal(lit.info[:, :15], ded.info[:, :15], equal_nan=True)
+    assert ded.info[:, 15].sum() < lit.info[:, 15].sum()  # fewer iterations executed

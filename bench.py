@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py — ADMM CSI solves/sec (16x16 antennas, fixed iterations) on N B200s, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0|config3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0|config3|config5]
 
 A "step" is one pass of the hot path over one batch of synthetic instances (the same batch every
 step; dense inputs of a batch exceed the 126 MB L2).  Workloads (BASELINE.json configs):
   config1 (default)  inferLowRank_Nuclear, M in {32,64,128,256} x SNR in {0,10,20,30} dB
   config0            inferLowRankV4_multi (what A2only dispatches to), M=64, SNR 20 dB
   config3            MyPhaseLift (TFOCS trace-LS, MyPhaseLift.m defaults: maxIts 4000, tol 1e-10), M=128, 20 dB
+  config5            inferLowRankV4_multi on 32x32 antennas (n = 1024, general kernel), synthetic 2-bit codebook
 Fixed-iteration mode (ADMM workloads): tol_rel = tol_abs = 0, maxiter = 500.
 N>1: launched under torchrun, one rank per GPU, trials sharded (weak scaling), max-over-ranks time,
 one NCCL all-reduce of the NMSE statistics tensor after the timed region.
@@ -39,6 +40,9 @@ WORKLOADS = {
                     desc="config3: MyPhaseLift (TFOCS AT, maxIts 4000, tol 1e-10, restart 200, lambda 0.05), 16x16, "
                          "M=128, SNR 20 dB"),
 }
+WORKLOADS["config5"] = dict(variant="V4_MULTI", Ms=[190], snrs=[20.0], tx=32, rx=32,
+                            desc="config5: inferLowRankV4_multi, 32x32 antennas (n = 1024), synthetic 2-bit random "
+                                 "codebook (Generate_random_beam.m:31-34; none is shipped), M=190, SNR 20 dB")
 PL_METRIC = "PhaseLift CSI solves/sec (16x16 ant, M=128, MyPhaseLift.m defaults)"
 
 
@@ -46,13 +50,17 @@ def build_instances(wl, trials_per_cell, first_trial):
     """trials_per_cell instances for every (M, SNR) cell; trial t of a cell uses SeedSequence child
     first_trial + t, so the set is independent of the rank count."""
     from twoace_b200 import harness as hz
-    cb = hz.load_codebook()
+    tx, rx = wl.get("tx", 16), wl.get("rx", 16)
+    if (tx, rx) == (16, 16):
+        cb = hz.load_codebook()
+    else:   # no codebook is shipped for other array sizes: 2-bit random beams, fixed seed
+        cb = hz._ROOTS[hz.random_beam_codes(np.random.default_rng(20231017), 4096, tx * rx)]
     insts, cells = [], []
     ci = 0
     for M in wl["Ms"]:
         for snr in wl["snrs"]:
             batch = hz.make_batch(trials_per_cell, cb, M, snr, base_seed=hz.BASE_SEED + 7919 * ci,
-                                  first_trial=first_trial)
+                                  first_trial=first_trial, Nt=tx, Nr=rx)
             insts += batch
             cells += [ci] * trials_per_cell
             ci += 1
@@ -66,7 +74,7 @@ def stage_flops(n, m, r, tx, nuclear):
     return core + (16 * n * r * r if nuclear else 16 * tx * n * r)
 
 
-def solve_flops(insts, stage_words, variant, cc_frac=0.95, rmax=20):
+def solve_flops(insts, stage_words, variant, cc_frac=0.95, rmax=20, N=N, TX=TX):
     """Sum over instances and stages of iterations actually executed x per-iteration flops."""
     T = 3 if variant == "V4_MULTI" else 1
     nuc = variant == "NUCLEAR"
@@ -86,7 +94,8 @@ def solve_flops(insts, stage_words, variant, cc_frac=0.95, rmax=20):
 def _oracle_worker(job):
     from threadpoolctl import threadpool_limits
     from oracle import admm
-    variant, A, B, train_idx = job
+    variant, A, B, train_idx = job[:4]
+    TX, RX = job[4] if len(job) > 4 else (16, 16)
     p = admm.Params().fixed_iters()
     with threadpool_limits(limits=1):
         t0 = time.perf_counter()
@@ -100,11 +109,11 @@ def _oracle_worker(job):
     return X, dt
 
 
-def run_oracle_pool(variant, insts, cores):
+def run_oracle_pool(variant, insts, cores, dims=(16, 16)):
     """Time the NumPy oracle on `insts`, trial-parallel over `cores` single-threaded processes
     (the analogue of the reference's parfor, Vs_M_par.m:145).  Returns (X list, wall seconds)."""
     import multiprocessing as mp
-    jobs = [(variant, i.A, i.B, i.train_idx) for i in insts]
+    jobs = [(variant, i.A, i.B, i.train_idx, dims) for i in insts]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         pool.map(_noop, range(cores))            # start the workers (imports) outside the timed region
@@ -194,7 +203,8 @@ def reference_arm(args, wl, rank, world):
     with ctx.Pool(cores) as pool:
         pool.map(_noop, range(cores))
         for s in range(args.warmup + args.steps):
-            jobs = [(wl["variant"], i.A, i.B, i.train_idx) for i in order[s * per_step:(s + 1) * per_step]]
+            jobs = [(wl["variant"], i.A, i.B, i.train_idx, (wl.get("tx", 16), wl.get("rx", 16)))
+                    for i in order[s * per_step:(s + 1) * per_step]]
             t0 = time.perf_counter()
             pool.map(_oracle_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
@@ -232,6 +242,8 @@ def ours_arm(args, wl, rank, local_rank, world):
         ctx.set_option("dedup_nuclear_rerun", 1)
     variant = getattr(tw, wl["variant"])
     T = 3 if wl["variant"] == "V4_MULTI" else 1
+    TX, RX = wl.get("tx", 16), wl.get("rx", 16)
+    N = TX * RX
     tpc = args.trials_per_cell
     insts, cells, n_cells = build_instances(wl, tpc, rank * tpc)   # weak scaling: tpc trials per cell per GPU
     nb = len(insts)
@@ -305,7 +317,7 @@ def ours_arm(args, wl, rank, local_rank, world):
     stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info, met), dev if world > 1 else None)
 
     # ---- roofline of the dominant kernel (admm_stage_kernel), live CUDA-event durations
-    flops_step = solve_flops(insts, sw, wl["variant"])
+    flops_step = solve_flops(insts, sw, wl["variant"], N=N, TX=TX)
     peak = ctx.fp64_peak_tflops()
     achieved = flops_step * args.steps / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -349,7 +361,7 @@ def ours_arm(args, wl, rank, local_rank, world):
         cores = os.cpu_count() or 1
         sel = sample_instances(insts, cells, n_cells, per_cell=max(1, min(tpc, math.ceil(cores / n_cells))))
         sub = [insts[i] for i in sel]
-        Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)))
+        Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)), (TX, RX))
         cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": min(cores, len(sub)),
                         "kind": "port",
                         "sample": f"{len(sub)} of the step's {nb} instances ({len(sub) // n_cells} per (M,SNR) cell), "
@@ -359,7 +371,8 @@ def ours_arm(args, wl, rank, local_rank, world):
         nmse_delta = g - o
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC if N == 256 else METRIC.replace("16x16", f"{TX}x{RX}"), "value": value,
+                "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step_per_gpu": nb,
@@ -584,7 +597,7 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.trials_per_cell is None:
-        args.trials_per_cell = {"config1": 32, "config0": 512, "config3": 296}[args.workload]
+        args.trials_per_cell = {"config1": 32, "config0": 512, "config3": 296, "config5": 148}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -109,7 +109,7 @@ int twoace_solve_batch(twoace_ctx* ctx, int variant, int mem, int nb, int tx, in
                        double* info, double* stage_words);
 
 /* Register a codebook shared by all instances: rows x n complex, column-major (the `cb` variable of
- * codebook/codebook_mat/*.mat), host or device per `mem`.  Kept on the device until replaced. */
+ * codebook/codebook_mat, the .mat files), host or device per `mem`.  Kept on the device until replaced. */
 int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, const double* cb);
 
 /* Same as twoace_solve_batch with A_b = row_scale * cb[cb_rows_b, :] (the row selection of

@@ -143,3 +143,69 @@ def aligned_rel_err(x: np.ndarray, x_ref: np.ndarray) -> float:
     ph = np.exp(1j * np.angle(np.vdot(x, x_ref)))
     den = np.linalg.norm(x_ref)
     return float(np.linalg.norm(x * ph - x_ref) / (den if den > 0 else 1.0))
+
+
+# ----------------------------------------------------------------------------------- parity bundles
+_BUNDLE_PARAMS = ("lam", "r", "mu0", "rho", "cc_frac", "tol_rel", "tol_abs", "maxiter")
+
+
+def export_bundle(path: str, A_list, B_list, tx, rx, solver, train_idx_list=None, params=None) -> None:
+    """Write a MATLAB v5 .mat bundle that tools/matlab/run_bundle.m replays through the UNMODIFIED reference
+    (the only way to pin parity against the reference needs a MATLAB licence; this is the file
+    format both sides share).  ``solver``: reference function name(s) ('inferLowRankV4', 'inferLowRankV4_multi',
+    'inferLowRank_Nuclear', 'inferLowRankV3', 'inferLowRankV2', 'inferLowRank', 'MyPhaseLift'), one per instance
+    or one for all.  ``train_idx_list``: per instance the 0-based randsample draws [T, floor(m*cc_frac)]
+    (stored 1-based, drawn order); ``params``: object with the fields of lib.Params (defaults if None).
+    For 'MyPhaseLift' B holds the intensities."""
+    from scipy.io import savemat
+    nb = len(A_list)
+    solvers = [solver] * nb if isinstance(solver, str) else list(solver)
+    txs = np.broadcast_to(np.asarray(tx, dtype=np.float64), (nb,))
+    rxs = np.broadcast_to(np.asarray(rx, dtype=np.float64), (nb,))
+    pv = [0.0, 20.0, 1e-3, 1.03, 0.95, 1e-4, 1e-8, 500.0]
+    if params is not None:
+        pv = [float(getattr(params, k)) for k in _BUNDLE_PARAMS]
+    A = np.empty((nb, 1), dtype=object)
+    B = np.empty((nb, 1), dtype=object)
+    tr = np.empty((nb, 1), dtype=object)
+    sv = np.empty((nb, 1), dtype=object)
+    for b in range(nb):
+        A[b, 0] = np.asarray(A_list[b], dtype=np.complex128)
+        B[b, 0] = np.asarray(B_list[b], dtype=np.float64).reshape(-1, 1)
+        draws = [] if train_idx_list is None else np.atleast_2d(np.asarray(train_idx_list[b]))
+        cell = np.empty((1, len(draws)), dtype=object)
+        for t, d in enumerate(draws):
+            cell[0, t] = (np.asarray(d, dtype=np.float64) + 1.0).reshape(-1, 1)
+        tr[b, 0] = cell
+        sv[b, 0] = solvers[b]
+    savemat(path, {"A": A, "B": B, "train_idx": tr, "solver": sv, "tx": txs.reshape(-1, 1),
+                   "rx": rxs.reshape(-1, 1), "params": np.tile(np.asarray(pv), (nb, 1))}, format="5")
+
+
+def import_bundle(path: str) -> dict:
+    """Read a bundle written by export_bundle back (0-based draws) -- also what tools/pin_parity.py uses."""
+    from scipy.io import loadmat
+    S = loadmat(path, squeeze_me=False)
+    nb = S["A"].shape[0]
+    out = {"A": [], "B": [], "train_idx": [], "solver": [], "tx": S["tx"].reshape(-1).astype(int),
+           "rx": S["rx"].reshape(-1).astype(int), "params": S["params"]}
+    for b in range(nb):
+        out["A"].append(np.asarray(S["A"][b, 0], dtype=np.complex128))
+        out["B"].append(np.asarray(S["B"][b, 0], dtype=np.float64).reshape(-1))
+        cell = S["train_idx"][b, 0]
+        draws = [np.asarray(cell[0, t]).reshape(-1).astype(np.int64) - 1 for t in range(cell.shape[1])] \
+            if cell.size else []
+        out["train_idx"].append(np.array(draws, dtype=np.int32) if draws else np.zeros((0, 0), np.int32))
+        out["solver"].append(str(np.asarray(S["solver"][b, 0]).reshape(-1)[0]))
+    return out
+
+
+def import_reference_results(path: str) -> dict:
+    """Read the result file saved by tools/matlab/run_bundle.m: X (list of n-vectors), Y, quality."""
+    from scipy.io import loadmat
+    S = loadmat(path, squeeze_me=False)
+    nb = S["X"].shape[0]
+    return {"X": [np.asarray(S["X"][b, 0], dtype=np.complex128).reshape(-1) for b in range(nb)],
+            "Y": [np.asarray(S["Y"][b, 0], dtype=np.complex128).reshape(-1) for b in range(nb)],
+            "quality": np.asarray(S["quality"], dtype=np.float64).reshape(-1),
+            "matlab_version": str(np.asarray(S.get("matlab_version", [""])).reshape(-1)[0])}

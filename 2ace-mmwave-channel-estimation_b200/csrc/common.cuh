@@ -278,7 +278,9 @@ template <int D>
 struct JacobiTab {
   static constexpr int ROUNDS = D - 1, HALF = D / 2;
   static constexpr int PAIRS_BYTES = ROUNDS * HALF * 2, TAB_BYTES = ROUNDS * D;
-  static constexpr int BYTES = (PAIRS_BYTES + 2 * TAB_BYTES + 15) / 16 * 16;
+  static constexpr int TABLES = (PAIRS_BYTES + 2 * TAB_BYTES + 15) / 16 * 16;
+  static constexpr int PRM_BYTES = 2 * HALF * 4 * 8;   // rotation parameters (c, sg.x, sg.y, |sg|^2), double-buffered
+  static constexpr int BYTES = TABLES + PRM_BYTES;
 };
 
 template <int D>
@@ -409,6 +411,107 @@ __device__ inline int jacobi_small(cd* Ga, cd* Gb, cd* V, const unsigned char* m
 }
 
 // ------------------------------------------------------------------------------------------
+// Software-pipelined variant of jacobi_small: same rotations, same element formula, bit-identical results.
+// The serial part of a round is the derivation of the next rotations (FP32 angle + FP64 renormalisation,
+// ~400 cycles of dependent latency), which needs only THREE updated entries per pair.  Warp 0 ("pilot") computes
+// those entries for the pairs of the NEXT round straight from the old matrix and the current rotations, derives
+// the next rotations and publishes them in shared memory, while warps 1..7 apply the current rotations to all
+// D*D entries and to V.  One barrier per round; the derivation is off the critical path of the update.
+// mem: JacobiTab<D>::BYTES (tables followed by the double-buffered rotation parameters).
+template <int D>
+__device__ inline int jacobi_small_p(cd* Ga, cd* Gb, cd* V, unsigned char* mem, bool init_v,
+                                     int max_sweeps = 30, int* any_rotation = nullptr, double skip_below = 0.0,
+                                     double floor_rel = 1.0e-18, double stop_sin2 = 1.0e-16, int nrounds = D - 1) {
+  static_assert(D % 2 == 0 && D <= 32, "unsupported dimension");
+  constexpr int H = D / 2, E = D * D, NB = NT - 32;
+  const unsigned char* pairs = mem;
+  const unsigned char* tab = mem + JacobiTab<D>::PAIRS_BYTES;
+  const unsigned char* tab2 = tab + JacobiTab<D>::TAB_BYTES;
+  double* prm = reinterpret_cast<double*>(mem + JacobiTab<D>::TABLES);   // [2][H][4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (init_v) {
+    for (int e = tid; e < E; e += NT) V[e] = cmk((e % D == e / D) ? 1.0 : 0.0, 0.0);
+  }
+  double g = 0.0;
+#pragma unroll
+  for (int q = 0; q < D; ++q) g = fmax(g, fabs(Ga[(D + 1) * q].x));
+  const double floor_abs = floor_rel * g;
+  const double floor2 = floor_abs * floor_abs;
+  const double inv_g = (g > 0.0) ? 1.0 / g : 0.0;
+  if (tid < H) {   // rotations of round 0 from the matrix as given
+    const int p = pairs[2 * tid], q = pairs[2 * tid + 1];
+    double c;
+    cd sg;
+    jacobi_rot_sg(Ga[(D + 1) * p].x, Ga[(D + 1) * q].x, Ga[p + D * q], floor2, inv_g, c, sg, skip_below);
+    prm[4 * tid] = c; prm[4 * tid + 1] = sg.x; prm[4 * tid + 2] = sg.y; prm[4 * tid + 3] = cabs2(sg);
+  }
+  __syncthreads();
+  cd* Gin = Ga;
+  cd* Gout = Gb;
+  int sweeps = 0, cur = 0;
+  // entry (i, j) of J' G J for the rotations P of round rd, from the read-only Gin
+  auto elem = [&](const cd* Gi, const double* P, int rd, int i, int j) -> cd {
+    const int ti = tab[D * rd + i], tj = tab[D * rd + j];
+    const int pi = tab2[D * rd + i], pj = tab2[D * rd + j];
+    const int ka = ti & 127, kb = tj & 127;
+    const double ca = P[4 * ka], cb = P[4 * kb];
+    const cd sa = cmk(P[4 * ka + 1], P[4 * ka + 2]), sb = cmk(P[4 * kb + 1], P[4 * kb + 2]);
+    const cd gij = Gi[i + D * j], gipj = Gi[i + D * pj], gpij = Gi[pi + D * j], gpipj = Gi[pi + D * pj];
+    const cd ap = (ti & 128) ? cmk(sa.x, -sa.y) : cmk(-sa.x, -sa.y);
+    const cd bp = (tj & 128) ? sb : cmk(-sb.x, sb.y);
+    const cd t1 = cadd(cscale(gij, cb), cmul(bp, gipj));
+    const cd t2 = cadd(cscale(gpij, cb), cmul(bp, gpipj));
+    cd n = cadd(cscale(t1, ca), cmul(ap, t2));
+    if (i == j) n.y = 0.0;
+    return n;
+  };
+  while (sweeps < max_sweeps) {
+    double smax = 0.0;
+    for (int rd = 0; rd < nrounds; ++rd) {
+      const double* P = prm + cur * (4 * H);
+      double* Pn = prm + (cur ^ 1) * (4 * H);
+      if (warp == 0) {
+        if (lane < H) {
+          smax = fmax(smax, P[4 * lane + 3]);
+          const int rn = (rd + 1 == nrounds) ? 0 : rd + 1;
+          const int p = pairs[2 * (H * rn + lane)], q = pairs[2 * (H * rn + lane) + 1];
+          const cd npp = elem(Gin, P, rd, p, p), nqq = elem(Gin, P, rd, q, q), npq = elem(Gin, P, rd, p, q);
+          double c;
+          cd sg;
+          jacobi_rot_sg(npp.x, nqq.x, npq, floor2, inv_g, c, sg, skip_below);
+          Pn[4 * lane] = c; Pn[4 * lane + 1] = sg.x; Pn[4 * lane + 2] = sg.y; Pn[4 * lane + 3] = cabs2(sg);
+        }
+      } else {
+        const int bt = tid - 32;
+        for (int e = bt; e < E; e += NB) Gout[e] = elem(Gin, P, rd, e % D, e / D);
+        const unsigned char* pr = pairs + 2 * H * rd;
+        for (int it = bt; it < H * D; it += NB) {
+          const int kv = it / D, iv = it - kv * D;
+          const double cv = P[4 * kv];
+          const cd sv = cmk(P[4 * kv + 1], P[4 * kv + 2]);
+          const int pv = pr[2 * kv], qv = pr[2 * kv + 1];
+          const cd vp = V[iv + D * pv], vq = V[iv + D * qv];
+          V[iv + D * pv] = csub(cscale(vp, cv), cmulc(sv, vq));
+          V[iv + D * qv] = cadd(cmul(sv, vp), cscale(vq, cv));
+        }
+      }
+      __syncthreads();
+      cd* t = Gin; Gin = Gout; Gout = t;
+      cur ^= 1;
+    }
+    ++sweeps;
+    const int big = __syncthreads_or(smax > stop_sin2);
+    if (any_rotation) *any_rotation = big;
+    if (!big) break;
+  }
+  if (Gin != Ga) {
+    for (int e = tid; e < E; e += NT) Ga[e] = Gb[e];
+    __syncthreads();
+  }
+  return sweeps;
+}
+
+// ------------------------------------------------------------------------------------------
 // Block Jacobi for a d x d Hermitian matrix in global memory (d up to a few hundred): 16-wide index
 // blocks, round-robin over block pairs; each pair (I, J) is a 32 x 32 subproblem solved in shared memory by
 // one sweep of jacobi_small<32> (accumulating its rotation Q), after which Q is applied to the block
@@ -447,7 +550,7 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
       S[e] = (i < d && j < d) ? G[i + (size_t)ldg * j] : cmk(0.0, 0.0);
     }
     __syncthreads();
-    const int sw = jacobi_small<D2>(S, Sb, Q, tab, true, max_sweeps, nullptr, 0.0, 1.0e-18, stop_sin2);
+    const int sw = jacobi_small_p<D2>(S, Sb, Q, tab, true, max_sweeps, nullptr, 0.0, 1.0e-18, stop_sin2);
     for (int e = tid; e < D2 * D2; e += NT) {
       const int i = e % D2, j = e / D2;
       if (i < d && j < d) G[i + (size_t)ldg * j] = S[e];
@@ -516,8 +619,8 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
         const long long tp0 = prof ? clock64() : 0;
         // round 0 is a perfect matching of the blocks: the full 32 x 32 ordering there sweeps the pairs inside
         // every diagonal block once per sweep; all other block pairs only need their cross pairs
-        if (rd == 0) jacobi_small<D2>(S, Sb, Q, tab, true, 1, &big, 0.0, 1.0e-18, stop_sin2);
-        else jacobi_small<D2>(S, Sb, Q, tabx, true, 1, &big, 0.0, 1.0e-18, stop_sin2, B);
+        if (rd == 0) jacobi_small_p<D2>(S, Sb, Q, tab, true, 1, &big, 0.0, 1.0e-18, stop_sin2);
+        else jacobi_small_p<D2>(S, Sb, Q, tabx, true, 1, &big, 0.0, 1.0e-18, stop_sin2, B);
         if (prof) prof[0] += clock64() - tp0;
         rotated |= big;
         // write the rotated diagonal/off-diagonal blocks back

@@ -48,7 +48,7 @@ __host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
   b += 3 * (size_t)FN * RL * sizeof(cd);                    // X Z N
   b += 4 * (size_t)d.maxm * RL * sizeof(cd);                // Y M WT AX
   b += 4 * (size_t)d.ds * d.ds * sizeof(cd);                // G P U xG
-  b += 8 * sizeof(cd) + 1280 + 32 * sizeof(double);         // LUTs, Jacobi tables + rotation params
+  b += 8 * sizeof(cd) + 2048 + 32 * sizeof(double);         // LUTs, Jacobi tables + rotation params
   b += (size_t)(d.ds / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
   b += (size_t)d.maxm * sizeof(double) * 5;                 // Bs, xrow[2], rowtot[2]
   b += (2 * XS_SCAL + 2 * SMALL_DMAX) * sizeof(double);     // xsc (double-buffered), xcol (double-buffered)
@@ -92,7 +92,7 @@ __device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
   s.P = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
   s.U = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);    // persistent across iterations (warm start)
   s.xG = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
-  s.pairs = (unsigned char*)p; p += 1280;   // Jacobi pair / element tables (D = 16 or 20)
+  s.pairs = (unsigned char*)p; p += 2048;   // JacobiTab<16 or 20>::BYTES: pair / element tables + rotation parameters
   s.jprm = (double*)p; p += 32 * sizeof(double);
   s.lut = (cd*)p; p += 8 * sizeof(cd);
   const int h = d.ds / 2 + 2;
@@ -630,8 +630,9 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
       // rounding noise of ~1e-16 max|diag| in every entry, so the numerically null cluster of a low-rank Z
       // can never be resolved below that; chasing it costs ~3 extra sweeps per call and changes the retained
       // singular values by at most r * 1e-15 relative to the largest one.
-      sw = jacobi_small<20>(sm.G, sm.P, sm.U, sm.pairs, !warm, 30, nullptr, 0.0, 1.0e-15);
-      if (tid == 0) sm.ifl[2] += 1;
+      const long long tj0 = clock64();
+      sw = jacobi_small_p<20>(sm.G, sm.P, sm.U, sm.pairs, !warm, 30, nullptr, 0.0, 1.0e-15);
+      if (tid == 0) { sm.ifl[2] += 1; sm.sc[20] += (double)(clock64() - tj0); }
     } else {
       sw = jacobi_heig(sm.G, r, sm.U, r, r, true, sm.js);
     }

@@ -541,39 +541,28 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
     }
   } else {
     const int ccap = (int)(stage_cap / FN);     // whole columns per staging chunk (>= 1)
-    // ---- Gram rows of the local columns: G[c0 + cl, c'] = sum_k conj(z[k, c0+cl]) z[k, c']
-    for (int idx = tid; idx < RL * RL; idx += NT) {   // local x local
-      const int cl = idx % RL, c2 = idx / RL;
-      cd g0 = cmk(0.0, 0.0), g1 = g0, g2 = g0, g3 = g0;
-      const cd* za = sm.N + FN * cl;
-      const cd* zb = sm.N + FN * c2;
-      for (int k = 0; k < FN; k += 4) {
-        cfmac(g0, za[k], zb[k]); cfmac(g1, za[k + 1], zb[k + 1]);
-        cfmac(g2, za[k + 2], zb[k + 2]); cfmac(g3, za[k + 3], zb[k + 3]);
-      }
-      sm.xG[(c0 + cl) + r * (c0 + c2)] = cmk((g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y));
-    }
-    if constexpr (CS > 1) {
-      for (int pr = 1; pr < CS; ++pr) {
-        const int rk = (rank + pr) % CS;
-        const cd* rem = peer_ptr<cd, CS>(sm.N, rk);
-        for (int cb = 0; cb < RL; cb += ccap) {
-          const int nc = min(ccap, RL - cb);
-          __syncthreads();
-          for (int idx = tid; idx < nc * FN; idx += NT) stage[idx] = rem[(size_t)FN * cb + idx];
-          __syncthreads();
-          for (int idx = tid; idx < RL * nc; idx += NT) {
-            const int cl = idx % RL, cc = idx / RL;
-            cd g0 = cmk(0.0, 0.0), g1 = g0, g2 = g0, g3 = g0;
-            const cd* za = sm.N + FN * cl;
-            const cd* zb = stage + FN * cc;
-            for (int k = 0; k < FN; k += 4) {
-              cfmac(g0, za[k], zb[k]); cfmac(g1, za[k + 1], zb[k + 1]);
-              cfmac(g2, za[k + 2], zb[k + 2]); cfmac(g3, za[k + 3], zb[k + 3]);
-            }
-            sm.xG[(c0 + cl) + r * (rk * RL + cb + cc)] =
-                cmk((g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y));
-          }
+    // ---- Gram rows of the local columns: G[c0 + cl, c'] = sum_k conj(z[k, c0+cl]) z[k, c'] for ALL c' (local and
+    // remote).  One warp per column c': lane l takes k = l, l + 32, ...; the column -- read straight from the
+    // owner's shared memory (DSMEM), every element exactly once -- is multiplied with the RL local columns, then
+    // the RL partial sums are reduced over the warp.  No staging buffer, no block barrier.
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int col = warp; col < r; col += NW) {
+        const int own = col / RL;
+        const cd* zc = (own == rank ? sm.N : peer_ptr<cd, CS>(sm.N, own)) + FN * (col - own * RL);
+        cd acc[RL];
+#pragma unroll
+        for (int cl = 0; cl < RL; ++cl) acc[cl] = cmk(0.0, 0.0);
+#pragma unroll 2
+        for (int k = lane; k < FN; k += 32) {
+          const cd z = zc[k];
+#pragma unroll
+          for (int cl = 0; cl < RL; ++cl) cfmac(acc[cl], sm.N[k + FN * cl], z);
+        }
+#pragma unroll
+        for (int cl = 0; cl < RL; ++cl) {
+          const double gx = warp_sum(acc[cl].x), gy = warp_sum(acc[cl].y);
+          if (lane == 0) sm.xG[(c0 + cl) + r * col] = cmk(gx, gy);
         }
       }
     }

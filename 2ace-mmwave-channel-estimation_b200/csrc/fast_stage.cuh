@@ -1138,7 +1138,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
 }
 
 template <int RL, int CS>
-__global__ void __launch_bounds__(NT, (RL <= 5) ? 2 : 1)
+__global__ void __launch_bounds__(NT, (RL == 1) ? 2 : 1)
 fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FastSmem<RL> sm = fast_carve<RL>(smem_raw, fd);

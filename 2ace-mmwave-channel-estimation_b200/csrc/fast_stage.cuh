@@ -540,7 +540,7 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
       sm.Z[idx] = cmk(0.0, 0.0);
     }
   } else {
-    const int ccap = (int)(stage_cap / FN);     // whole columns per staging chunk (>= 1)
+    (void)stage; (void)stage_cap;   // (remote columns are read in place; no staging buffer any more)
     // ---- Gram rows of the local columns: G[c0 + cl, c'] = sum_k conj(z[k, c0+cl]) z[k, c'] for ALL c' (local and
     // remote).  One warp per column c': lane l takes k = l, l + 32, ...; the column -- read straight from the
     // owner's shared memory (DSMEM), every element exactly once -- is multiplied with the RL local columns, then
@@ -663,19 +663,17 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
       }
     }
     if constexpr (CS > 1) {
+      // remote columns straight from their owner's shared memory (coalesced over k, every element read once)
       for (int pr = 1; pr < CS; ++pr) {
         const int rk = (rank + pr) % CS;
         const cd* rem = peer_ptr<cd, CS>(sm.N, rk);
-        for (int cb = 0; cb < RL; cb += ccap) {
-          const int nc = min(ccap, RL - cb);
-          __syncthreads();
-          for (int idx = tid; idx < nc * FN; idx += NT) stage[idx] = rem[(size_t)FN * cb + idx];
-          __syncthreads();
-          for (int cc = 0; cc < nc; ++cc) {
-            const cd z = stage[tid + FN * cc];
+        cd zr[RL];
 #pragma unroll
-            for (int c2 = 0; c2 < RL; ++c2) cfma(acc[c2], z, sm.P[(rk * RL + cb + cc) + r * (c0 + c2)]);
-          }
+        for (int cc = 0; cc < RL; ++cc) zr[cc] = rem[tid + FN * cc];
+#pragma unroll
+        for (int cc = 0; cc < RL; ++cc) {
+#pragma unroll
+          for (int c2 = 0; c2 < RL; ++c2) cfma(acc[c2], zr[cc], sm.P[(rk * RL + cc) + r * (c0 + c2)]);
         }
       }
     }

@@ -127,6 +127,7 @@ struct PlSmem {
   unsigned char* tab;      // JacobiTab<32>
   double *b, *Ax, *Az, *Ay, *Axo, *Azo, *g;   // measurement-space vectors [maxm]
   double* sv;              // kept shifted eigenvalues [n]
+  double* sacc;            // [n] diagonal of U' z_old U (shifted eigenvalues of the accepted prox, by column)
   int* idx;                // their column indices [n]
   double* red;             // reduction scratch [4 * NW]
   int* ib;                 // small int scratch [16]
@@ -137,7 +138,7 @@ __host__ __device__ inline size_t pl_smem_bytes(int n, int maxm) {
   b += 3 * 32 * 32 * sizeof(cd);
   b += 2 * JacobiTab<32>::BYTES + 64;
   b += 7 * (size_t)((maxm + 1) / 2 * 2) * sizeof(double);
-  b += (size_t)n * sizeof(double) + (size_t)n * sizeof(int);
+  b += 2 * (size_t)n * sizeof(double) + (size_t)n * sizeof(int);
   b += 4 * NW * sizeof(double) + 16 * sizeof(int);
   return b + 64;
 }
@@ -156,6 +157,7 @@ __device__ inline PlSmem pl_carve(unsigned char* p, int n, int maxm) {
   s.g = dp + 6 * mv;
   dp += 7 * mv;
   s.sv = dp; dp += n;
+  s.sacc = dp; dp += n;
   s.red = dp; dp += 4 * NW;
   s.idx = reinterpret_cast<int*>(dp);
   s.ib = s.idx + n;
@@ -206,15 +208,15 @@ __device__ inline void lifted_forward(const cd* At, int m, int d, const cd* M, c
 // Hermitian eigendecomposition W = V diag(lam) V' warm-started from the basis U.  W is overwritten by the
 // rotated matrix (eigenvalues on its diagonal); V receives the eigenvectors.  T: d x d scratch.
 __device__ inline int warm_eig(cd* W, const cd* U, cd* V, cd* T, int d, const PlSmem& sm, long long* tc = nullptr,
-                               double act_thr = -INFINITY) {
+                               double act_thr = -INFINITY, bool rotated = false) {
   const int tid = threadIdx.x;
   const long long t0 = clock64();
-  // T = W U
-  cta_gemm<false, true>(d, d, d, [&](int i, int k) { return W[i + (size_t)d * k]; },
+  // T = W U   (skipped when the caller already formed U' W U in W)
+  if (!rotated) cta_gemm<false, true>(d, d, d, [&](int i, int k) { return W[i + (size_t)d * k]; },
                         [&](int k, int j) { return U[k + (size_t)d * j]; },
                         [&](int i, int j, cd v) { T[i + (size_t)d * j] = v; }, sm.sA, sm.sB);
   // W <- U' T (Hermitian up to rounding; the diagonal is made real)
-  cta_gemm<true, true, true>(d, d, d, [&](int i, int k) { return cconj(U[k + (size_t)d * i]); },
+  if (!rotated) cta_gemm<true, true, true>(d, d, d, [&](int i, int k) { return cconj(U[k + (size_t)d * i]); },
                              [&](int k, int j) { return T[k + (size_t)d * j]; },
                              [&](int i, int j, cd v) {
                                if (i == j) v.y = 0.0;
@@ -332,6 +334,7 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
   }
   double f_y = f_x;
   bool y_is_fresh = true;          // A_y / f_y valid for the current y (tfocs_AT.m:49 clears them when theta < 1)
+  bool zold_diag = false;          // U[uc]' z_old U[uc] = diag(sacc): z_old is the prox output whose basis U[uc] is
   int cntr_Ay = 0, cntr_Ax = 0;
   bool force_Ax = false;           // cntr_Ax = Inf (tfocs_backtrack.m:18)
   bool backtrack_simple = true;
@@ -383,6 +386,29 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
       const double step = 1.0 / (theta * L);                         // :59
       const double tau = o.lam * step;                               // prox_trace.m:77
       long long t0 = clock64();
+      cd* V = ws.U[uc ^ 1];
+      long long t1;
+      if (zold_diag) {
+        // z_old = U diag(sacc) U' exactly (it was built from these columns), so
+        //   U' W U = diag(sacc) - step * (A U)' diag(g) (A U):  one m x d x d and one Hermitian d x d x m product
+        // instead of forming W and transforming it (three products)
+        const cd* U = ws.U[uc];
+        cta_gemm<false, true>(m, d, d, [&](int i, int k) { return ws.At[i + (size_t)m * k]; },
+                              [&](int k, int j) { return U[k + (size_t)d * j]; },
+                              [&](int i, int j, cd v) { ws.T[i + (size_t)m * j] = v; }, sm.sA, sm.sB);
+        cta_gemm<true, true, true>(d, d, m,
+                                   [&](int i, int k) { return cscale(cconj(ws.T[k + (size_t)m * i]), sm.g[k]); },
+                                   [&](int k, int j) { return ws.T[k + (size_t)m * j]; },
+                                   [&](int i, int j, cd v) {
+                                     cd w = cmk(-step * v.x, -step * v.y);
+                                     if (i == j) { w.x += sm.sacc[i]; w.y = 0.0; }
+                                     ws.W[i + (size_t)d * j] = w;
+                                     if ((i / PG_TM) != (j / PG_TM)) ws.W[j + (size_t)d * i] = cconj(w);
+                                   }, sm.sA, sm.sB);
+        t1 = clock64();
+        tc[0] += t1 - t0;
+        n_sweeps += warm_eig(ws.W, ws.U[uc], V, ws.T, d, sm, &tc[1], tau, true);
+      } else {
       // W = z_old - step * A' diag(g) A                               (:60 argument, initializeLinopPR.m:65)
       cta_gemm<true, true, true>(d, d, m,
                                  [&](int i, int k) { return cscale(cconj(ws.At[k + (size_t)m * i]), sm.g[k]); },
@@ -394,10 +420,11 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
                                    ws.W[i + (size_t)d * j] = w;
                                    if ((i / PG_TM) != (j / PG_TM)) ws.W[j + (size_t)d * i] = cconj(w);   // mirrored tile
                                  }, sm.sA, sm.sB);
-      cd* V = ws.U[uc ^ 1];
-      long long t1 = clock64();
+      t1 = clock64();
       tc[0] += t1 - t0;
       n_sweeps += warm_eig(ws.W, ws.U[uc], V, ws.T, d, sm, &tc[1], tau);   // prox_trace.m:92
+      }
+      zold_diag = false;   // U[uc ^ 1] now belongs to this attempt; set again when the attempt is accepted
       uc ^= 1;
       t0 = clock64();
       n_prox++;
@@ -543,6 +570,12 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
     }
     xc ^= 1;
     zc ^= 1;
+    // the accepted z is V_+ diag(s) V_+' with V = U[uc]: remember its diagonal form for the next prox
+    for (int i = tid; i < d; i += NT) sm.sacc[i] = 0.0;
+    __syncthreads();
+    for (int k = tid; k < rank; k += NT) sm.sacc[sm.idx[k]] = sm.sv[k];
+    __syncthreads();
+    zold_diag = true;
     // ---- tfocs_iterate.m:8-33
     n_iter++;
     const double norm_x = sqrt(norm_x2), norm_dx = sqrt(norm_dx2);
@@ -563,6 +596,7 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
       for (int i = tid; i < m; i += NT) { sm.Ay[i] = sm.Ax[i]; sm.Az[i] = sm.Ax[i]; }
       __syncthreads();
       y_is_fresh = false;   // f_y = f_x: recomputed from A_y = A_x
+      zold_diag = false;    // z = x is not diagonal in the basis U
     }
   }
 

@@ -52,6 +52,21 @@ def load_codebook(name: str = "random_probe_cb_16x16") -> np.ndarray:
     return _ROOTS[load_codebook_codes(name)]
 
 
+def load_codebook_mat(path: str, var: str = "cb") -> np.ndarray:
+    """Read a reference codebook file (codebook/codebook_mat/*.mat, MATLAB v5, variable ``cb``: rows x Nt*Nr
+    complex, or the 3-D directional layout which is flattened to rows x n) the way the entry points receive it
+    (cb_amp .* exp(1j*cb_angle), ...simulation_A2only.m:120).  Entries within 1e-12 of a 4th root of unity are
+    snapped to it, so that twoace_set_codebook finds exact 2-bit phase codes."""
+    from scipy.io import loadmat
+    cb = np.asarray(loadmat(path)[var], dtype=np.complex128)
+    if cb.ndim == 3:
+        cb = cb.reshape(-1, cb.shape[-1])
+    k = np.round(np.angle(cb) / (np.pi / 2)).astype(np.int64) % 4
+    snapped = _ROOTS[k] * np.abs(cb)
+    close = np.abs(cb - snapped) <= 1e-12 * np.maximum(np.abs(cb), 1e-300)
+    return np.where(close, snapped, cb)
+
+
 def random_beam_codes(rng: np.random.Generator, rows: int, n: int, phase_bit: int = 2) -> np.ndarray:
     """Random Np-phase beam codes (Generate_random_beam.m:31-34, Np = Phase_Bit^2)."""
     return rng.integers(0, phase_bit ** 2, size=(rows, n), dtype=np.uint8)

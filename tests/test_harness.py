@@ -49,3 +49,17 @@ def test_metrics():
     assert hz.aligned_rel_err(np.exp(1.3j) * x, x) < 1e-14
     assert abs(hz.nmse(np.zeros(32) + 1e-30, x) - 1) < 1      # garbage -> ~0 dB
     assert hz.nmse_db([0.1, 0.1]) == -10.0
+
+
+def test_load_codebook_mat_round_trip(tmp_path, codebook):
+    """A codebook written the way the reference ships it (.mat v5, variable cb) loads back with exact phases."""
+    from scipy.io import savemat
+    from twoace_b200 import harness as hz
+    noisy = codebook[:50] * (1 + 0j)
+    noisy = np.abs(noisy) * np.exp(1j * np.angle(noisy))          # cos(pi/2) = 6e-17 residues, as in the shipped files
+    path = str(tmp_path / "cb.mat")
+    savemat(path, {"cb": noisy}, format="5")
+    cb = hz.load_codebook_mat(path)
+    assert cb.shape == (50, 256) and np.array_equal(cb, codebook[:50])
+    savemat(path, {"cb": noisy.reshape(5, 10, 256)}, format="5")
+    assert hz.load_codebook_mat(path).shape == (50, 256)

@@ -825,6 +825,7 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
     const double res_dual = mu * sqrt(nAtYd2 + nZd2);
     res_comb = sqrt(nJM2 + nJN2 + nYd2 + nZd2);
     iters = it;
+    if (tk.trace != nullptr && threadIdx.x == 0) tk.trace[it - 1] = res_comb;
     if (prm.need_dual) {
       const double mx1 = fmax(sqrt(nAX2), sqrt(nY2)), mx2 = fmax(sqrt(nX2), sqrt(nZ2));
       const double th_prim = prm.tol_abs * sqrt((double)(m + n) * r) + prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2);

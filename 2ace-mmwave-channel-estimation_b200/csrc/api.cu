@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,9 +35,15 @@ struct twoace_ctx {
   int opt_fast = 1;      // 1: use the shared-memory cluster kernel when a launch is eligible
   int opt_fast_cs = 2;   // cluster size for the r = 20 stages (2 or 4)
   int opt_dedup_nuclear = 0;   // 1: do not re-execute the (bit-identical) rank-one rerun of inferLowRank_Nuclear
-  int64_t fast_launches = 0;
+  int opt_cache_sinv = 1;   // 1: the stages of a trial share one (I + A A')^-1 (computed by the first of them)
+  int opt_tensor = 1;    // 1: exact int8 tensor-core (tcgen05) A-products in the cluster kernel, 0: FP64 SIMT products
+  int64_t fast_launches = 0, tc_launches = 0;
+  double* trace_user = nullptr;   // optional residual-trace sink of the next solves (twoace_set_trace)
+  int trace_mem = 0;
+  size_t trace_cap = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
+  std::vector<std::string> stage_labels;   // one per stage_events entry (TWOACE_TRACE_LAUNCHES=1 prints them)
 };
 
 #define CK(call)                                                                              \
@@ -160,13 +167,17 @@ static int stage_grid(twoace_ctx* ctx, size_t smem, int ntasks, int* grid) {
   return 0;
 }
 
-template <int RL, int CS>
+constexpr size_t SMEM_LIMIT = (size_t)227 * 1024;
+
+template <int RL, int CS, bool TC>
 static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const DevParams& prm, FastDims fd,
                          bool* launched) {
   *launched = false;
-  auto kern = fast_stage_kernel<RL, CS>;
-  const size_t smem = fast_smem_bytes<RL>(fd);
-  if (smem > 227 * 1024) return 0;
+  auto kern = fast_stage_kernel<RL, CS, TC>;
+  size_t smem = fast_smem_bytes<RL>(fd);
+  if (smem > SMEM_LIMIT) return 0;
+  // the tensor-core kernel allocates all 512 tensor-memory columns: keep it alone on its SM
+  if (TC) smem = std::max(smem, (size_t)117 * 1024);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(NT, 1, 1);
@@ -196,9 +207,14 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
     ctx->stage_events.emplace_back(e0, e1);
+    char lb[160];
+    snprintf(lb, sizeof lb, "fast_stage_kernel<%d,%d,%s> tasks %d clusters %d maxm %d smem %zu nslot %d n1 %d", RL, CS,
+             TC ? "tc" : "simt", ntasks, ncl, fd.maxm, smem, fd.tc.nslot, fd.tc.n1);
+    ctx->stage_labels.emplace_back(lb);
   }
   ctx->launches++;
   ctx->fast_launches++;
+  if (TC) ctx->tc_launches++;
   *launched = true;
   return 0;
 }
@@ -244,54 +260,76 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
     ctx->stage_events.emplace_back(e0, e1);
+    char lb[160];
+    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d", tasks.size(), grid, dm.maxm, dm.maxr);
+    ctx->stage_labels.emplace_back(lb);
   }
   ctx->launches++;
   return 0;
 }
 
+// Shared-memory geometry of the cluster kernel for an r = 20 task with m rows; false when it does not fit.
+template <int RL>
+static bool fast_dims(int m, bool nuc, bool tc, FastDims* out) {
+  FastDims f = {};
+  f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
+  f.nuclear = nuc ? 1 : 0; f.ds = nuc ? 20 : 16;
+  if (tc) { if (!fast_tc_layout<RL>(f, SMEM_LIMIT)) return false; }
+  else if (fast_smem_bytes<RL>(f) > SMEM_LIMIT) return false;
+  if (out) *out = f;
+  return true;
+}
+
 // One InferADMM launch.  Tasks that qualify for the shared-memory cluster kernel (16x16, quantised A,
-// r in {20,1}, m <= 256, V4 ArgMinZ) are split off, so the kernel an instance runs on never depends on
-// its batch mates.
+// r in {20,1}, m <= 256) are split off and grouped by kernel configuration; the configuration of a task is
+// decided by ITS OWN m (which layout fits in shared memory), never by its batch mates.
 static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
                         int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
-  // groups: r = 20 on cluster size 2, r = 20 on cluster size 4, r = 1; the cluster size of an r = 20 task
-  // is decided by ITS OWN m (does the RL = 10 layout fit in shared memory?), never by the batch
-  std::vector<StageTask> grp[3], gen;
+  // groups: 0 = <10,2> tensor-core, 1 = <5,4> tensor-core, 2 = <10,2> SIMT, 3 = <5,4> SIMT, 4 = r = 1
+  std::vector<StageTask> grp[5], gen;
   bool nuc = false;
   for (const StageTask& t : tasks) nuc = nuc || t.nuclear;     // a launch is all-nuclear or all-V4
-  auto fits2 = [nuc](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
-                              f.nuclear = nuc; f.ds = nuc ? 20 : 16;
-                              return fast_smem_bytes<10>(f) <= (size_t)227 * 1024; };
-  auto fits4 = [nuc](int m) { FastDims f; f.maxm = m; f.mw = (m + 15) / 16; f.r = 20; f.ws_stride = 0;
-                              f.nuclear = nuc; f.ds = nuc ? 20 : 16;
-                              return fast_smem_bytes<5>(f) <= (size_t)227 * 1024; };
+  const bool tc = ctx->opt_tensor != 0;
   for (const StageTask& t : tasks) {
     if (!fast_eligible(ctx, t, n, tx, rx)) { gen.push_back(t); continue; }
-    if (t.r == 1) { grp[2].push_back(t); continue; }
+    if (t.r == 1) { grp[4].push_back(t); continue; }
     const bool want2 = ctx->opt_fast_cs == 2;
-    if (want2 && fits2(t.m)) grp[0].push_back(t);
-    else if (fits4(t.m)) grp[1].push_back(t);
-    else if (fits2(t.m)) grp[0].push_back(t);
+    const bool f2t = tc && fast_dims<10>(t.m, nuc, true, nullptr), f4t = tc && fast_dims<5>(t.m, nuc, true, nullptr);
+    const bool f2 = fast_dims<10>(t.m, nuc, false, nullptr), f4 = fast_dims<5>(t.m, nuc, false, nullptr);
+    if (want2 && f2t) grp[0].push_back(t);
+    else if (f4t) grp[1].push_back(t);
+    else if (f2t) grp[0].push_back(t);
+    else if (want2 && f2) grp[2].push_back(t);
+    else if (f4) grp[3].push_back(t);
+    else if (f2) grp[2].push_back(t);
     else gen.push_back(t);
   }
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < 5; ++g) {
     std::vector<StageTask>& ft = grp[g];
     if (ft.empty()) continue;
     // longest tasks first: clusters pick tasks round-robin, so this balances the tail of the launch
     std::stable_sort(ft.begin(), ft.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
-    FastDims fd;
-    fd.maxm = 1;
-    for (const StageTask& t : ft) fd.maxm = std::max(fd.maxm, t.m);
-    fd.mw = (fd.maxm + 15) / 16; fd.r = (g == 2) ? 1 : 20; fd.ws_stride = 0;
-    fd.nuclear = nuc ? 1 : 0; fd.ds = (nuc && g != 2) ? 20 : 16;
+    int maxm = 1;
+    for (const StageTask& t : ft) maxm = std::max(maxm, t.m);
+    FastDims fd = {};
+    bool ok = true;
+    if (g == 4) {
+      fd.maxm = maxm; fd.mw = (maxm + 15) / 16; fd.r = 1; fd.ws_stride = 0; fd.nuclear = nuc ? 1 : 0; fd.ds = 16;
+    } else if (g == 0 || g == 2) ok = fast_dims<10>(maxm, nuc, g == 0, &fd);
+    else ok = fast_dims<5>(maxm, nuc, g == 1, &fd);
+    if (!ok) FAIL(TWOACE_E_CUDA, "internal: cluster kernel layout (group %d, maxm %d)", g, maxm);
     const StageTask* dt = nullptr;
     int rc = upload_tasks(ctx, ft, cursor, &dt);
     if (rc) return rc;
     bool launched = false;
-    if (g == 2) rc = launch_fast_t<1, 1>(ctx, dt, (int)ft.size(), prm, fd, &launched);
-    else if (g == 0) rc = launch_fast_t<10, 2>(ctx, dt, (int)ft.size(), prm, fd, &launched);
-    else rc = launch_fast_t<5, 4>(ctx, dt, (int)ft.size(), prm, fd, &launched);
+    switch (g) {
+      case 0: rc = launch_fast_t<10, 2, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+      case 1: rc = launch_fast_t<5, 4, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+      case 2: rc = launch_fast_t<10, 2, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+      case 3: rc = launch_fast_t<5, 4, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+      default: rc = launch_fast_t<1, 1, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+    }
     if (rc) return rc;
     if (!launched) FAIL(TWOACE_E_CUDA, "cluster kernel launch configuration rejected (group %d, maxm %d)", g, fd.maxm);
   }
@@ -389,6 +427,7 @@ struct ChunkIn {
   const int32_t* train_idx;  // host
   twoace_params p;
   cd* dX; cd* dY; double* dQ; double* dInfo; double* dStage;  // device outputs (dInfo/dStage may be null)
+  double* dTrace;            // device, [nb][nstage][maxiter] or nullptr
 };
 
 static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
@@ -415,7 +454,9 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
     mtr[b] = (int)std::floor((double)m * in.p.cc_frac);
     mte[b] = m - mtr[b];
     if (mtr[b] < 1 || mte[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: empty train or test split", b);
-    rb[b] = std::min(std::min((int)in.p.r, m), n);
+    // r = min([r m n]) (:12); versions 1-3 re-evaluate it inside inferLowRankImpl with m = m_train, BEFORE their
+    // spectral init (inferLowRankV3.m:198-224), V4 / _multi / _Nuclear initialise outside with the full-m clamp
+    rb[b] = std::min(std::min((int)in.p.r, older ? mtr[b] : m), n);
     maxr = std::max(maxr, rb[b]);
     a_off[b + 1] = a_off[b] + (size_t)m * n;
     b_off[b + 1] = b_off[b] + m;
@@ -474,6 +515,11 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   const bool try_codes = ctx->opt_fast && n == FN && in.tx == FTX && in.rx == FTX;
   const size_t o_codes = (dense && try_codes) ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
   const size_t o_qflag = (dense && try_codes) ? bp.take((size_t)nb * sizeof(int)) : 0;
+  // per-instance store of (I + A_train A_train')^-1: the stages of a trial (over-parameterised, refinement and their
+  // rank-one reruns) share the training rows, so only the first of them inverts (instances on the cluster kernel)
+  std::vector<size_t> sv_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) sv_off[b + 1] = sv_off[b] + ((try_codes && ctx->opt_cache_sinv && mtr[b] <= 256) ? (size_t)mtr[b] * mtr[b] : 0);
+  const size_t o_sinv = sv_off[nb] ? bp.take(sv_off[nb] * sizeof(cd)) : 0;
   int rc = ensure(ctx, ctx->arena, bp.off + 256);
   if (rc) return rc;
   char* base = (char*)ctx->arena.p;
@@ -585,13 +631,17 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.sbr = 1; a.rank_one = pass ? 1 : prof; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
         a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
+        a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass) * in.p.maxiter : nullptr;
         a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
         a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
+        if (use_codes && sv_off[b + 1] > sv_off[b]) { a.sinv = (cd*)(base + o_sinv) + sv_off[b]; a.sinv_state = pass ? 1 : 0; }
         StageTask& s2 = sb[b];
         s2 = a;
+        if (s2.sinv) s2.sinv_state = 1;
         s2.X0 = d_Xa + (size_t)b * xstride; s2.Xout = d_xb + (size_t)b * n; s2.Yout = d_yb + b_off[b];
         s2.sbr = 0;
         s2.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass + 1) * STAGE_SCAL;
+        s2.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass + 1) * in.p.maxiter : nullptr;
         OrthoTask& o = ot[b];
         o.X = d_Xa + (size_t)b * xstride; o.r = rb[b]; o.active = a.active; o.active_expect = 1;
         QualTask& q = qt[b];
@@ -634,6 +684,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.sbr = 1; a.rank_one = prof; a.nuclear = nuclear; a.rank_one_ptr = older ? nullptr : &d_ctl[b].use_rank_one;
       a.active = refine_if_good ? &d_ctl[b].refine_on : nullptr; a.active_expect = 1;
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
+      a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + (nstage - 1)) * in.p.maxiter : nullptr;
       a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
       a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
       FinalTask& f = ft[b];
@@ -729,6 +780,16 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
   rc = dev_out(ctx, st, mem, quality, (size_t)nb * sizeof(double), &dQ); if (rc) return rc;
   rc = dev_out(ctx, st, mem, info, (size_t)nb * TWOACE_INFO_WORDS * sizeof(double), &dI); if (rc) return rc;
   rc = dev_out(ctx, st, mem, stage_words, (size_t)nb * nstage * STAGE_SCAL * sizeof(double), &dS); if (rc) return rc;
+  void* dT = nullptr;
+  const size_t trace_n = (size_t)nb * nstage * p.maxiter;
+  if (ctx->trace_user) {
+    if (trace_n > ctx->trace_cap) FAIL(TWOACE_E_INVALID, "trace buffer holds %zu doubles, this call needs %zu", ctx->trace_cap, trace_n);
+    rc = dev_out(ctx, st, ctx->trace_mem, ctx->trace_user, (trace_n + 1) * sizeof(double), &dT); if (rc) return rc;
+    if (ctx->trace_mem == TWOACE_MEM_DEVICE && (trace_n & 1)) FAIL(TWOACE_E_INVALID, "device trace buffers need an even element count (nb * stages * maxiter = %zu)", trace_n);
+    fill_nan_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>((cd*)dT, (trace_n + 1) / 2);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
 
   size_t ao = 0, bo = 0, to = 0;
   for (int b0 = 0; b0 < nb; b0 += ctx->chunk) {
@@ -742,6 +803,7 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
     in.dX = (cd*)dX + (size_t)b0 * n; in.dY = (cd*)dY + bo; in.dQ = (double*)dQ + b0;
     in.dInfo = dI ? (double*)dI + (size_t)b0 * TWOACE_INFO_WORDS : nullptr;
     in.dStage = dS ? (double*)dS + (size_t)b0 * nstage * STAGE_SCAL : nullptr;
+    in.dTrace = dT ? (double*)dT + (size_t)b0 * nstage * p.maxiter : nullptr;
     rc = solve_chunk(ctx, in);
     if (rc) return rc;
     for (int b = b0; b < b0 + cnt; ++b) {
@@ -754,7 +816,17 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
   rc = host_back(ctx, mem, quality, dQ, (size_t)nb * sizeof(double)); if (rc) return rc;
   rc = host_back(ctx, mem, info, dI, (size_t)nb * TWOACE_INFO_WORDS * sizeof(double)); if (rc) return rc;
   rc = host_back(ctx, mem, stage_words, dS, (size_t)nb * nstage * STAGE_SCAL * sizeof(double)); if (rc) return rc;
-  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  if (dT) { rc = host_back(ctx, ctx->trace_mem, ctx->trace_user, dT, trace_n * sizeof(double)); if (rc) return rc; }
+  if (mem == TWOACE_MEM_HOST || (dT && ctx->trace_mem == TWOACE_MEM_HOST)) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_set_trace(twoace_ctx* ctx, int mem, double* trace, int64_t capacity) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  if (trace && capacity < 1) FAIL(TWOACE_E_INVALID, "trace capacity must be positive");
+  ctx->trace_user = trace; ctx->trace_mem = mem; ctx->trace_cap = trace ? (size_t)capacity : 0;
   return TWOACE_OK;
 }
 
@@ -889,6 +961,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     std::vector<PrepTask> pt(nb);
     for (int b = 0; b < nb; ++b) {
       PrepTask& t = pt[b];
+      t = PrepTask{};
       t.A_cm = (const cd*)dA + a_off[b]; t.A_rm = d_Arm + a_off[b]; t.cb = nullptr; t.cbrows = nullptr;
       t.row_scale = 1.0; t.B = (const double*)dB + b_off[b]; t.m = m[b]; t.ctl = d_ctl + b;
     }
@@ -976,6 +1049,7 @@ extern "C" int twoace_spectral_init_batch(twoace_ctx* ctx, int mem, int nb, int 
     std::vector<PrepTask> pt(nb);
     for (int b = 0; b < nb; ++b) {
       PrepTask& t = pt[b];
+      t = PrepTask{};
       t.A_cm = (const cd*)dA + a_off[b]; t.A_rm = d_Arm + a_off[b]; t.cb = nullptr; t.cbrows = nullptr;
       t.row_scale = 1.0; t.B = (const double*)dB + b_off[b]; t.m = m[b]; t.ctl = d_ctl + b;
     }
@@ -1151,9 +1225,13 @@ extern "C" int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t*
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   double tot = 0.0;
+  const bool trace = getenv("TWOACE_TRACE_LAUNCHES") != nullptr;
+  size_t li = 0;
   for (auto& pr : ctx->stage_events) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    if (trace) fprintf(stderr, "[twoace] %9.3f ms  %s\n", ms, li < ctx->stage_labels.size() ? ctx->stage_labels[li].c_str() : "stage kernel");
+    ++li;
     tot += ms;
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
@@ -1161,6 +1239,7 @@ extern "C" int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t*
   if (stage_ms) *stage_ms = tot;
   if (stage_launches) *stage_launches = (int64_t)ctx->stage_events.size();
   ctx->stage_events.clear();
+  ctx->stage_labels.clear();
   return TWOACE_OK;
 }
 
@@ -1213,8 +1292,11 @@ extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   else if (k == "fast_cs") { if (value != 2 && value != 4) FAIL(TWOACE_E_INVALID, "fast_cs must be 2 or 4"); ctx->opt_fast_cs = value; }
   else if (k == "chunk") { if (value < 1) FAIL(TWOACE_E_INVALID, "chunk must be >= 1"); ctx->chunk = value; }
   else if (k == "dedup_nuclear_rerun") ctx->opt_dedup_nuclear = value ? 1 : 0;
+  else if (k == "tensor") ctx->opt_tensor = value ? 1 : 0;
+  else if (k == "cache_sinv") ctx->opt_cache_sinv = value ? 1 : 0;
   else FAIL(TWOACE_E_INVALID, "unknown option %s", key);
   return TWOACE_OK;
 }
 
 extern "C" int64_t twoace_fast_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->fast_launches : 0; }
+extern "C" int64_t twoace_tensor_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->tc_launches : 0; }

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "admm_stage.cuh"
+#include "tc_prod.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -36,26 +37,12 @@ struct FastDims {
   int ds;            // shared eig dimension: 16 (V4: tx x tx) or max(16, r) (nuclear: r x r)
   int nuclear;
   size_t ws_stride;  // global workspace elements (cd) per cluster
+  TcDims tc;         // tensor-core products (tc.on == 0: FP64 SIMT products)
 };
 
 __host__ __device__ inline size_t fast_ws_elems(const FastDims& d) {
-  return (size_t)d.maxm * d.maxm + (size_t)FN * d.r;   // Sinv | AtY
-}
-
-template <int RL>
-__host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
-  size_t b = 0;
-  b += 3 * (size_t)FN * RL * sizeof(cd);                    // X Z N
-  b += 4 * (size_t)d.maxm * RL * sizeof(cd);                // Y M WT AX
-  b += 4 * (size_t)d.ds * d.ds * sizeof(cd);                // G P U xG
-  b += 8 * sizeof(cd) + 2048 + 32 * sizeof(double);         // LUTs, Jacobi tables + rotation params
-  b += (size_t)(d.ds / 2 + 2) * (sizeof(cd) + 2 * sizeof(double));
-  b += (size_t)d.maxm * sizeof(double) * 5;                 // Bs, xrow[2], rowtot[2]
-  b += (2 * XS_SCAL + 2 * SMALL_DMAX) * sizeof(double);     // xsc (double-buffered), xcol (double-buffered)
-  b += (16 * NW + 3 * SMALL_DMAX + 32) * sizeof(double);  // red, s2s, colsc, sc
-  b += (size_t)d.mw * 256 * 4 + (size_t)16 * d.maxm * 4;    // cki, cik
-  b += (size_t)d.maxm * sizeof(int) + 48 * sizeof(int);
-  return b + 256;
+  // Sinv | AtY | operand blocks of the tensor-core products (streaming mode)
+  return (size_t)d.maxm * d.maxm + (size_t)FN * d.r + (d.tc.on ? TC_AOP_BYTES / sizeof(cd) : 0);
 }
 
 template <int RL>
@@ -72,49 +59,120 @@ struct FastSmem {
   double* xsc;      // exchange: [2][XS_SCAL] scalars (parity double-buffered)
   double* xcol;     // exchange: [2][SMALL_DMAX] per-column objectives (owner writes its slots)
   double *red, *s2s, *colsc, *sc;
-  uint32_t* cki;    // [mw][256]   code(i = 16w + j, k) in bits 2j of cki[w*256 + k]
-  uint32_t* cik;    // [16][m]     code(i, k = 16w + j) in bits 2j of cik[w*m + i]
+  uint32_t* cki;    // [mw][256]   code(i = 16w + j, k) in bits 2j of cki[w*256 + k]   (SIMT products only)
+  uint32_t* cik;    // [16][m]     code(i, k = 16w + j) in bits 2j of cik[w*m + i]     (tensor-core mode: setup only,
+                    //             aliases the B operand)
   int* rows_s;
   int* ifl;
+  // tensor-core products
+  unsigned char* tc_bs;    // B operand
+  unsigned char* tc_ov;    // overlay region (== G): ring slots [0, n1)
+  unsigned char* tc_ex;    // ring slots [n1, nslot)
+  uint64_t* tc_bars;
+  uint32_t* tc_tslot;
+  size_t bytes;            // total carved
 };
 
+// Shared-memory layout of the fast kernel; fast_smem_bytes() is the size of the same carve.
+// G | P | xG are contiguous (the "overlay": dead outside ArgMinZ, so the tensor-core products use it as ring slots).
 template <int RL>
-__device__ inline FastSmem<RL> fast_carve(unsigned char* p, const FastDims& d) {
+__host__ __device__ inline FastSmem<RL> fast_carve(unsigned char* base, const FastDims& d) {
   FastSmem<RL> s;
-  s.X = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
-  s.Z = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
-  s.N = (cd*)p; p += (size_t)FN * RL * sizeof(cd);
-  s.Y = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
-  s.M = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
-  s.WT = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
-  s.AX = (cd*)p; p += (size_t)d.maxm * RL * sizeof(cd);
-  s.G = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
-  s.P = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
-  s.U = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);    // persistent across iterations (warm start)
-  s.xG = (cd*)p; p += (size_t)d.ds * d.ds * sizeof(cd);
-  s.pairs = (unsigned char*)p; p += 2048;   // JacobiTab<16 or 20>::BYTES: pair / element tables + rotation parameters
-  s.jprm = (double*)p; p += 32 * sizeof(double);
-  s.lut = (cd*)p; p += 8 * sizeof(cd);
+  unsigned char* p = base;
+  auto take = [&p](size_t bytes, size_t align) {
+    size_t a = (size_t)p;
+    a = (a + align - 1) / align * align;
+    unsigned char* q = (unsigned char*)a;
+    p = q + bytes;
+    return q;
+  };
+  s.X = (cd*)take((size_t)FN * RL * sizeof(cd), 16);
+  s.Z = (cd*)take((size_t)FN * RL * sizeof(cd), 16);
+  s.N = (cd*)take((size_t)FN * RL * sizeof(cd), 16);
+  s.Y = (cd*)take((size_t)d.maxm * RL * sizeof(cd), 16);
+  s.M = (cd*)take((size_t)d.maxm * RL * sizeof(cd), 16);
+  s.WT = (cd*)take((size_t)d.maxm * RL * sizeof(cd), 16);
+  s.AX = (cd*)take((size_t)d.maxm * RL * sizeof(cd), 16);
+  const size_t gpx = 3 * (size_t)d.ds * d.ds * sizeof(cd);
+  const size_t ovb = d.tc.on ? (size_t)d.tc.ov_bytes : gpx;
+  s.tc_ov = take(ovb, 128);
+  s.G = (cd*)s.tc_ov;
+  s.P = s.G + (size_t)d.ds * d.ds;
+  s.xG = s.P + (size_t)d.ds * d.ds;
+  s.U = (cd*)take((size_t)d.ds * d.ds * sizeof(cd), 16);   // persistent across iterations (warm start)
+  s.pairs = take(2048, 16);   // JacobiTab<16 or 20>::BYTES: pair / element tables + rotation parameters
+  s.jprm = (double*)take(32 * sizeof(double), 16);
+  s.lut = (cd*)take(8 * sizeof(cd), 16);
   const int h = d.ds / 2 + 2;
-  s.js.e = (cd*)p; p += (size_t)h * sizeof(cd);
-  s.js.cs = (double*)p; p += (size_t)h * sizeof(double);
-  s.js.sn = (double*)p; p += (size_t)h * sizeof(double);
-  s.Bs = (double*)p; p += (size_t)d.maxm * sizeof(double);
-  s.xrow = (double*)p; p += (size_t)2 * d.maxm * sizeof(double);
-  s.rowtot = (double*)p; p += (size_t)2 * d.maxm * sizeof(double);
-  s.xsc = (double*)p; p += 2 * XS_SCAL * sizeof(double);
-  s.xcol = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
-  s.red = (double*)p; p += 16 * NW * sizeof(double);
-  s.s2s = (double*)p; p += SMALL_DMAX * sizeof(double);
-  s.colsc = (double*)p; p += 2 * SMALL_DMAX * sizeof(double);
-  s.sc = (double*)p; p += 32 * sizeof(double);
-  s.cki = (uint32_t*)p; p += (size_t)d.mw * 256 * 4;
-  s.cik = (uint32_t*)p; p += (size_t)16 * d.maxm * 4;
-  s.rows_s = (int*)p; p += (size_t)d.maxm * sizeof(int);
-  s.ifl = (int*)p; p += 48 * sizeof(int);
+  s.js.e = (cd*)take((size_t)h * sizeof(cd), 16);
+  s.js.cs = (double*)take((size_t)h * sizeof(double), 8);
+  s.js.sn = (double*)take((size_t)h * sizeof(double), 8);
+  s.Bs = (double*)take((size_t)d.maxm * sizeof(double), 8);
+  s.xrow = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
+  s.rowtot = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
+  s.xsc = (double*)take(2 * XS_SCAL * sizeof(double), 8);
+  s.xcol = (double*)take(2 * SMALL_DMAX * sizeof(double), 8);
+  s.red = (double*)take(16 * NW * sizeof(double), 8);
+  s.s2s = (double*)take(SMALL_DMAX * sizeof(double), 8);
+  s.colsc = (double*)take(2 * SMALL_DMAX * sizeof(double), 8);
+  s.sc = (double*)take(32 * sizeof(double), 8);
+  s.rows_s = (int*)take((size_t)d.maxm * sizeof(int), 4);
+  s.ifl = (int*)take(48 * sizeof(int), 4);
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;
+  const size_t cik_bytes = (size_t)16 * d.maxm * 4;
+  if (d.tc.on) {
+    s.cki = nullptr;
+    s.tc_bs = take(cik_bytes > (size_t)TC_BS_BYTES ? cik_bytes : (size_t)TC_BS_BYTES, 128);
+    s.cik = (uint32_t*)s.tc_bs;
+    s.tc_bars = (uint64_t*)take((2 * TC_MAXSLOT + 1) * sizeof(uint64_t), 8);
+    s.tc_tslot = (uint32_t*)take(16, 4);
+    // the ring slots outside the overlay; 2 KB of slack behind them: a K-major read of a block with fewer than
+    // 128 rows per slab runs past its last slab (the rows it reads there land in unused accumulator lanes)
+    s.tc_ex = take((size_t)(d.tc.nslot - d.tc.n1) * d.tc.slot_bytes + 2048, 128);
+  } else {
+    s.cki = (uint32_t*)take((size_t)d.mw * 256 * 4, 16);
+    s.cik = (uint32_t*)take(cik_bytes, 16);
+    s.tc_bs = nullptr; s.tc_ex = nullptr; s.tc_bars = nullptr; s.tc_tslot = nullptr;
+  }
+  s.bytes = (size_t)(p - base);
   return s;
+}
+
+template <int RL>
+__host__ __device__ inline size_t fast_smem_bytes(const FastDims& d) {
+  // carve from a 1024-aligned dummy base (the kernel's dynamic shared memory is declared with that alignment)
+  return fast_carve<RL>((unsigned char*)(uintptr_t)1024, d).bytes + 128;
+}
+
+// Ring geometry of the tensor-core products for a launch with the given maxm: the overlay region holds n1 slots,
+// the rest of the ring takes what is left of `limit` bytes of shared memory.  Returns false when no slot fits.
+template <int RL>
+__host__ inline bool fast_tc_layout(FastDims& d, size_t limit) {
+  const int mt = (d.maxm + 127) / 128;
+  if (mt > 2) return false;
+  const int R = mt > 1 ? 128 : (d.maxm + 31) / 32 * 32;
+  const int nblk = 4 * mt;
+  const size_t gpx = 3 * (size_t)d.ds * d.ds * sizeof(cd);
+  d.tc.on = 1;
+  d.tc.slot_bytes = R * 128;
+  // try the overlay grown to one slot when the Gram buffers alone are smaller
+  for (int grow = 0; grow < 2; ++grow) {
+    size_t ov = gpx;
+    if (grow && ov < (size_t)d.tc.slot_bytes) ov = d.tc.slot_bytes;
+    ov = (ov + 127) / 128 * 128;
+    d.tc.ov_bytes = (int)ov;
+    d.tc.n1 = (int)std::min<size_t>(ov / d.tc.slot_bytes, (size_t)nblk);
+    d.tc.nslot = d.tc.n1;
+    const size_t base = fast_smem_bytes<RL>(d);
+    if (base > limit) continue;
+    // (up to nblk slots behind the overlay: with all of them the blocks stay resident for the whole stage)
+    const int extra = (int)std::min<size_t>((limit - base) / d.tc.slot_bytes, (size_t)nblk);
+    d.tc.nslot = std::min(d.tc.n1 + extra, TC_MAXSLOT);
+    if (d.tc.nslot >= 1 && (grow || d.tc.nslot >= 2)) return true;
+  }
+  d.tc.on = 0;
+  return d.tc.on != 0;
 }
 
 template <int CS>
@@ -235,36 +293,85 @@ __device__ __forceinline__ void prod_a(const uint32_t* cik, int m, const cd* V, 
 }
 
 // W = Sinv * R (R = T - A Q in `RW`, overwritten by W) and AX = T - W (T in `TAX`, overwritten by AX).
-// Sinv lives in global memory / L2.
-template <int RL>
-__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, cd* RW, cd* TAX) {
+// Sinv lives in global memory / L2 (m^2 x 16 B per iteration: the largest stream of the kernel).  Register tile of
+// NR = 4 (2 for RL = 10) rows x RL columns per thread: every R operand read from shared memory (a broadcast LDS.128)
+// feeds NR complex FMAs and the Sinv elements of a thread are NR x 16 contiguous bytes.  The reduction index j is split over ks
+// adjacent lanes (shuffle reduction); the Sinv values of the next two j are loaded while the current two are
+// multiplied, so eight independent L2 loads per thread are always in flight.
+template <int RL, int NR>
+__device__ __forceinline__ void prod_sinv_t(const cd* __restrict__ Sinv, int m, cd* RW, cd* TAX) {
   const int tid = threadIdx.x;
-  const int ks = ksplit_for(m, 8);
-  const int i = tid / ks, s = tid - i * ks;
-  const bool act = i < m;
-  cd acc[RL];
+  const int mq = (m + NR - 1) / NR;
+  const int ks = ksplit_for(mq, 16);
+  const int iq = tid / ks, s = tid - iq * ks;
+  const bool act = iq < mq;
+  int row[NR];
 #pragma unroll
-  for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+  for (int u = 0; u < NR; ++u) row[u] = min(NR * iq + u, m - 1);
+  cd acc[NR][RL];
+#pragma unroll
+  for (int u = 0; u < NR; ++u)
+#pragma unroll
+    for (int c = 0; c < RL; ++c) acc[u][c] = cmk(0.0, 0.0);
   if (act) {
-#pragma unroll 4
-    for (int j = s; j < m; j += ks) {
-      const cd a = Sinv[i + (size_t)m * j];
+    const int nj = (m - s + ks - 1) / ks;           // this lane's j: s, s + ks, ...
+    cd cur[2][NR], nxt[2][NR];
+    auto fetch = [&](cd (&dst)[2][NR], int q) {      // j indices q, q + 1 of this lane (clamped: the tail is masked below)
 #pragma unroll
-      for (int c = 0; c < RL; ++c) cfma(acc[c], a, RW[j + m * c]);
+      for (int h = 0; h < 2; ++h) {
+        const int j = s + ks * min(q + h, nj - 1);
+#pragma unroll
+        for (int u = 0; u < NR; ++u) dst[h][u] = __ldg(Sinv + row[u] + (size_t)m * j);
+      }
+    };
+    fetch(cur, 0);
+    for (int q = 0; q < nj; q += 2) {
+      if (q + 2 < nj) fetch(nxt, q + 2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (q + h < nj) {
+          const int j = s + ks * (q + h);
+#pragma unroll
+          for (int c = 0; c < RL; ++c) {
+            const cd r = RW[j + m * c];
+#pragma unroll
+            for (int u = 0; u < NR; ++u) cfma(acc[u][c], cur[h][u], r);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < NR; ++u) cur[h][u] = nxt[h][u];
     }
   }
-  group_reduce<RL>(acc, ks);
+#pragma unroll
+  for (int u = 0; u < NR; ++u) group_reduce<RL>(acc[u], ks);
   __syncthreads();            // every thread has finished reading R before it is overwritten by W
   if (act && s == 0) {
 #pragma unroll
-    for (int c = 0; c < RL; ++c) {
-      const int p = i + m * c;
-      const cd t = TAX[p];
-      RW[p] = acc[c];
-      TAX[p] = cmk(t.x - acc[c].x, t.y - acc[c].y);
+    for (int u = 0; u < NR; ++u) {
+      if (NR * iq + u < m) {
+#pragma unroll
+        for (int c = 0; c < RL; ++c) {
+          const int p = NR * iq + u + m * c;
+          const cd t = TAX[p];
+          RW[p] = acc[u][c];
+          TAX[p] = cmk(t.x - acc[u][c].x, t.y - acc[u][c].y);
+        }
+      }
     }
   }
   __syncthreads();
+}
+
+// Rows per thread by problem size: the wider tiles pay for their shuffle reduction only when m is large (measured
+// on B200, cycles per call at m = 30 / 60 / 121 / 243:  NR 1: ~6 k / 7 k / 19 k / 62 k,  NR 4: 8.4 k / 12.4 k / 20 k / 51 k).
+template <int RL>
+__device__ __forceinline__ void prod_sinv(const cd* __restrict__ Sinv, int m, cd* RW, cd* TAX) {
+  if (m > 128) prod_sinv_t<RL, (RL > 5 ? 2 : 4)>(Sinv, m, RW, TAX);
+  else if (m > 64) prod_sinv_t<RL, 2>(Sinv, m, RW, TAX);
+  else prod_sinv_t<RL, 1>(Sinv, m, RW, TAX);
 }
 
 // ArgMinZ (inferLowRankV4.m:402-464) + N update (:319-320) + X/Z norms.  Contains exactly one
@@ -706,9 +813,9 @@ __device__ inline void fast_argmin_z_nuclear(const FastDims& fd, const FastSmem<
   }
 }
 
-template <int RL, int CS>
+template <int RL, int CS, bool TC>
 __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const FastDims& fd,
-                                const FastSmem<RL>& sm, cd* wsg, int rank) {
+                                const FastSmem<RL>& sm, cd* wsg, int rank, TcCtx& tc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = tk.m;
   constexpr int r = RL * CS;
@@ -716,11 +823,52 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   const double cs = *tk.cscale;          // A_eff = cs * u
   const double bsc = *tk.bscale;
   const int rank_one = tk.rank_one_ptr ? *tk.rank_one_ptr : tk.rank_one;
-  cd* Sinv = wsg;
+  cd* Sinv = tk.sinv != nullptr ? tk.sinv : wsg;      // (I + A A')^-1: per-instance store or cluster workspace
+  const bool sinv_reuse = tk.sinv != nullptr && tk.sinv_state == 1;
+  const long long ttask0 = clock64();
   cd* AtY = wsg + (size_t)fd.maxm * fd.maxm;   // [256 x r], column c0+c owned by this CTA
   const cd* lut = sm.lut;
   const cd* lutc = sm.lut + 4;
   cd* scratch = sm.WT;                   // WT | AX (pivot row / column of the Gauss-Jordan inverse)
+  TcGeom tg = {};
+  if constexpr (TC) {
+    tg = tc_geom(m, tc.nslot_launch, tc.n1);
+    tc.nslot = tc.nslot_launch;
+    tc.wt_slot = -1;
+    if (!tg.resident) {
+      // streaming: one producer warp per slot (warps 1 .. NW-1); WT serves as one more slot while it is dead
+      // (single-pass products only: with RL = 10 the second column pass still needs WT)
+      tc.nslot = min(tc.nslot, NW - 2);
+      if (RL == TC_NC && (size_t)fd.maxm * RL * sizeof(cd) >= (size_t)tc.slot_bytes) { tc.wt_slot = tc.nslot; tc.nslot += 1; }
+    }
+    tc.premask = 0;
+    tc.aop = (unsigned char*)(wsg + (size_t)fd.maxm * fd.maxm + (size_t)FN * fd.r);
+  }
+  // store(i, c, sum_k u(i,k) V[k + 256 c]), c < RL: FP64 SIMT or exact int8 tensor-core product
+  auto product_a = [&](const cd* V, auto store) {
+    if constexpr (TC) {
+      for (int cb = 0; cb < RL; cb += TC_NC)
+        tc_product<false>(tc, tg, m, [&](int k, int c) { return V[k + FN * (cb + c)]; },
+                          [&](int i, int c, cd v) { store(i, cb + c, v); }, (uint32_t*)sm.red);
+    } else {
+      prod_a<RL>(sm.cik, m, V, lut, store);
+    }
+  };
+  // store(k, c, sum_i conj(u(i,k)) Op[i + m c]), every (k, c) exactly once, by the thread that owns it
+  auto product_ah = [&](const cd* Op, auto store) {
+    if constexpr (TC) {
+      for (int cb = 0; cb < RL; cb += TC_NC)
+        tc_product<true>(tc, tg, m, [&](int i, int c) { return Op[i + m * (cb + c)]; },
+                         [&](int k, int c, cd v) { store(k, cb + c, v); }, (uint32_t*)sm.red);
+    } else {
+      cd acc[RL];
+#pragma unroll
+      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
+      const int kk = prod_ah<RL>(sm.cki, m, Op, m, lutc, acc);
+#pragma unroll
+      for (int c = 0; c < RL; ++c) store(kk, c, acc[c]);
+    }
+  };
 
   // ---- stage-local copies
   if (tid < 4) {
@@ -739,7 +887,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     sm.cik[w * m + i] = tk.codes[(size_t)sm.rows_s[i] * 16 + w];
   }
   __syncthreads();
-  {
+  if constexpr (!TC) {
     const int k = tid;   // thread k packs code(i, k) for all i
     for (int w = 0; w * 16 < m; ++w) {
       uint32_t word = 0;
@@ -760,9 +908,11 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   }
   const double normB = sqrt(nb2);
 
-  // ---- S = I + A A' from exact phase counts (pairs split over the cluster), inverse by rank 0
+  // ---- S = I + A A' from exact phase counts (pairs split over the cluster), inverse by rank 0; skipped when an
+  // earlier stage of the same trial has left the inverse in the per-instance store (same rows, same scale)
   {
     const double cs2 = cs * cs;
+    if (!sinv_reuse)
     for (int idx = tid + NT * rank; idx < m * m; idx += NT * CS) {
       const int i = idx % m, j = idx / m;
       if (i >= j) {
@@ -783,9 +933,11 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
         if (i != j) Sinv[j + (size_t)m * i] = cmk(v.x, -v.y);
       }
     }
+    // operand blocks of the tensor-core products (the code copy `cik` is dead after this: it aliases the B operand)
+    if constexpr (TC) tc_build(tc, tg, sm.cik, m, tg.resident ? 0 : rank, tg.resident ? 1 : CS);
     __threadfence();
     cl_sync<CS>();
-    if (rank == 0) spd_inverse(Sinv, m, scratch, scratch + m);
+    if (rank == 0 && !sinv_reuse) spd_inverse(Sinv, m, scratch, scratch + m);
     __threadfence();
     cl_sync<CS>();
   }
@@ -798,7 +950,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   for (int idx = tid; idx < m * RL; idx += NT) sm.M[idx] = cmk(0.0, 0.0);
   __syncthreads();
   // AX = A X  (:278)
-  prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) { sm.AX[i + m * c] = cscale(v, cs); });
+  product_a(sm.X, [&](int i, int c, cd v) { sm.AX[i + m * c] = cscale(v, cs); });
   // rescale so |A X| matches |B|  (:279-286)
   if (tk.sbr) {
     double v[1] = {0.0};
@@ -868,14 +1020,9 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
   if (fd.nuclear) fast_argmin_z_nuclear<RL, CS>(fd, sm, rank, 1.0, true, sm.xsc + XS_SCAL - 1, stage, stage_cap, nz, &sweeps);
   else fast_argmin_z<RL, CS>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);
   __syncthreads();
-  if (prm.need_dual) {   // AtY = A' Y  (:289)
-    cd acc[RL];
-#pragma unroll
-    for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-    const int kk = prod_ah<RL>(sm.cki, m, sm.Y, m, lutc, acc);
-#pragma unroll
-    for (int c = 0; c < RL; ++c) AtY[kk + (size_t)FN * (c0 + c)] = cscale(acc[c], cs);
-  }
+  if constexpr (TC && CS > 1) cl_sync<CS>();   // peers have read this CTA's Gram partial: the overlay is free again
+  if (prm.need_dual)     // AtY = A' Y  (:289)
+    product_ah(sm.Y, [&](int k, int c, cd v) { AtY[k + (size_t)FN * (c0 + c)] = cscale(v, cs); });
 
   double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
   int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
@@ -900,23 +1047,17 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
       sm.X[idx] = cmk(fma(-nn.x, imu, z.x), fma(-nn.y, imu, z.y));
     }
     __syncthreads();
-    prod_a<RL>(sm.cik, m, sm.X, lut, [&](int i, int c, cd v) {     // R = T - A Q -> WT
+    product_a(sm.X, [&](int i, int c, cd v) {                      // R = T - A Q -> WT
       const cd t = sm.AX[i + m * c];
       sm.WT[i + m * c] = cmk(fma(-v.x, cs, t.x), fma(-v.y, cs, t.y));
     });
+    if constexpr (TC) tc_prefetch<true>(tc, tg, m);                    // the A' W blocks arrive during the S^-1 product
     prod_sinv<RL>(Sinv, m, sm.WT, sm.AX);                           // W -> WT, A X = T - W -> AX
-    {
-      cd acc[RL];
-#pragma unroll
-      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);  // X = Q + A' W
-#pragma unroll
-      for (int c = 0; c < RL; ++c) {
-        const int p = kk + FN * c;
-        const cd x = sm.X[p];
-        sm.X[p] = cmk(fma(acc[c].x, cs, x.x), fma(acc[c].y, cs, x.y));
-      }
-    }
+    product_ah(sm.WT, [&](int k, int c, cd v) {                    // X = Q + A' W
+      const int p = k + FN * c;
+      const cd x = sm.X[p];
+      sm.X[p] = cmk(fma(v.x, cs, x.x), fma(v.y, cs, x.y));
+    });
     __syncthreads();
     const long long tx1 = clock64();
     if (tid == 0) sm.sc[21] += (double)(tx1 - tx0);
@@ -1011,22 +1152,17 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     // ---- A'(Y - Y0) (:309): advances AtY in global memory; only feeds res_dual
     double pAtYd2 = 0.0, pAtY2 = 0.0;
     if (prm.need_dual) {
-      cd acc[RL];
-#pragma unroll
-      for (int c = 0; c < RL; ++c) acc[c] = cmk(0.0, 0.0);
-      const int kk = prod_ah<RL>(sm.cki, m, sm.WT, m, lutc, acc);
       double v[2] = {0.0, 0.0};
-#pragma unroll
-      for (int c = 0; c < RL; ++c) {
-        const size_t p = kk + (size_t)FN * (c0 + c);
-        const cd d = cscale(acc[c], cs);
+      product_ah(sm.WT, [&](int k, int c, cd acc) {
+        const size_t p = k + (size_t)FN * (c0 + c);
+        const cd d = cscale(acc, cs);
         cd a = AtY[p];
         a.x += d.x;
         a.y += d.y;
         AtY[p] = a;
         v[0] += cabs2(d);
         v[1] += cabs2(a);
-      }
+      });
       block_sum<2>(v, sm.red);
       pAtYd2 = v[0]; pAtY2 = v[1];
     }
@@ -1088,6 +1224,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     const double res_dual = mu * sqrt(nAtYd2 + nZd2);
     res_comb = sqrt(nJM2 + nJN2 + nYd2 + nZd2);
     iters = it;
+    if (tk.trace != nullptr && tid == 0 && rank == 0) tk.trace[it - 1] = res_comb;
     if (prm.need_dual) {
       const double mx1 = fmax(sqrt(nAX2), sqrt(nY2)), mx2 = fmax(sqrt(nX2), sqrt(nZ2));
       const double th_prim = prm.tol_abs * sqrt((double)(m + FN) * r) + prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2);
@@ -1131,23 +1268,44 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     tk.scal[SC_CONVERGED] = converged; tk.scal[SC_RES_COMB] = res_comb; tk.scal[SC_SWEEPS] = sweeps;
     tk.scal[9] = sm.sc[20]; tk.scal[10] = sm.sc[21]; tk.scal[11] = (double)(clock64() - tl0);
     tk.scal[12] = sm.sc[22]; tk.scal[13] = sm.sc[23]; tk.scal[14] = sm.sc[24];
+    tk.scal[15] = (double)(tl0 - ttask0);      // set-up: codes, S and its inverse, operand blocks, first ArgMinZ
   }
   cl_sync<CS>();   // no CTA leaves (or reuses its exchange buffers) while a peer may still read them
 }
 
-template <int RL, int CS>
+template <int RL, int CS, bool TC>
 __global__ void __launch_bounds__(NT, (RL == 1) ? 2 : 1)
 fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const FastSmem<RL> sm = fast_carve<RL>(smem_raw, fd);
+  extern __shared__ __align__(1024) unsigned char fast_smem_raw[];
+  const FastSmem<RL> sm = fast_carve<RL>(fast_smem_raw, fd);
   int rank = 0;
   if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
   const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
   cd* wsg = wsbase + (size_t)cid * fd.ws_stride;
+  TcCtx tc = {};
+  if constexpr (TC) {
+    // one CTA per SM (the host pads the shared-memory request): it owns all 512 tensor-memory columns
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < 2 * TC_MAXSLOT + 1; ++s) umma::mbar_init(sm.tc_bars + s, 1);
+      umma::mbar_fence_init();
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc512(sm.tc_tslot);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    tc.Bs = sm.tc_bs; tc.ov = sm.tc_ov; tc.ex = sm.tc_ex; tc.bars = sm.tc_bars; tc.tmem = *sm.tc_tslot;
+    tc.nslot_launch = fd.tc.nslot; tc.nslot = fd.tc.nslot; tc.n1 = fd.tc.n1; tc.slot_bytes = fd.tc.slot_bytes;
+    tc.wt = (unsigned char*)sm.WT; tc.wt_slot = -1;
+  }
   for (int t = cid; t < ntasks; t += ncl) {
     const StageTask tk = tasks[t];
     if (tk.active != nullptr && *tk.active != tk.active_expect) continue;   // cluster-uniform
-    run_fast<RL, CS>(tk, prm, fd, sm, wsg, rank);
+    run_fast<RL, CS, TC>(tk, prm, fd, sm, wsg, rank, tc);
+  }
+  if constexpr (TC) {
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_free512(tc.tmem);
   }
 }
 

@@ -39,6 +39,9 @@ struct StageTask {
   const double* cscale;   // device scalar: A_eff = (*cscale) * u(code)   (valid when codes != nullptr)
   double* scal;         // [STAGE_SCAL] per-task bookkeeping (may be nullptr)
   double2* state;       // optional dump of final [X Z N (n x r each) | Y M (m x r each)] (may be nullptr)
+  double2* sinv;        // optional per-instance store of (I + A A')^-1 (m x m) shared by the stages of one trial
+  int sinv_state;       // 0: compute it (into `sinv` when given, else the cluster workspace); 1: reuse `sinv`
+  double* trace;        // optional residual trace: trace[it-1] = res_comb of iteration it (:345), maxiter entries
 };
 
 enum {

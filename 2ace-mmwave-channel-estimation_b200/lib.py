@@ -23,7 +23,7 @@ EXPORTS = [
     "twoace_stream", "twoace_launch_count", "twoace_synchronize", "twoace_solve_batch",
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
-    "twoace_set_option", "twoace_fast_launch_count", "twoace_pl_default_opts", "twoace_phaselift_batch",
+    "twoace_set_option", "twoace_fast_launch_count", "twoace_tensor_launch_count", "twoace_set_trace", "twoace_pl_default_opts", "twoace_phaselift_batch",
     "twoace_metrics_batch",
 ]
 
@@ -123,6 +123,10 @@ def load() -> C.CDLL:
     lib.twoace_set_option.restype = C.c_int
     lib.twoace_fast_launch_count.argtypes = [vp]
     lib.twoace_fast_launch_count.restype = C.c_int64
+    lib.twoace_set_trace.argtypes = [vp, C.c_int, vp, C.c_int64]
+    lib.twoace_set_trace.restype = C.c_int
+    lib.twoace_tensor_launch_count.argtypes = [vp]
+    lib.twoace_tensor_launch_count.restype = C.c_int64
     lib.twoace_pl_default_opts.argtypes = [C.POINTER(PlOpts)]
     lib.twoace_pl_default_opts.restype = None
     lib.twoace_phaselift_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, dp, i32p, C.c_double, dp,
@@ -190,6 +194,21 @@ class Context:
     @property
     def fast_launch_count(self) -> int:
         return int(self.lib.twoace_fast_launch_count(self.h))
+
+    @property
+    def tensor_launch_count(self) -> int:
+        """Launches of the cluster kernel whose A-products ran on the tensor cores (tcgen05 kind::i8)."""
+        return int(self.lib.twoace_tensor_launch_count(self.h))
+
+    def set_trace(self, buf: "np.ndarray | None"):
+        """Attach a host float64 array that the next solve_batch calls fill with res_comb per (instance, stage,
+        iteration) -- see twoace_set_trace in include/twoace.h; None detaches it."""
+        self._trace = buf
+        if buf is None:
+            self.check(self.lib.twoace_set_trace(self.h, MEM_HOST, None, 0))
+        else:
+            assert buf.dtype == np.float64 and buf.flags.c_contiguous
+            self.check(self.lib.twoace_set_trace(self.h, MEM_HOST, buf.ctypes.data, buf.size))
 
     def set_timing(self, on: bool):
         self.check(self.lib.twoace_set_timing(self.h, int(bool(on))))

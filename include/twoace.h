@@ -73,7 +73,7 @@ typedef struct {
 /* stage bookkeeping words (per InferADMM call): 0 mu, 1 opt_obj, 2 iters, 3 opt_iter (1-based),
  * 4 opt_col (0-based, -1 for scale_by_row), 5 mu bumps, 6 converged, 7 last res_comb,
  * 8 Jacobi sweeps; 9..14 device clock cycles (fast kernel only): eigensolve, X update, whole loop,
- * Y/M update, ArgMinZ, exchange + best-iterate tail; 15 reserved. */
+ * Y/M update, ArgMinZ, exchange + best-iterate tail; 15 set-up cycles of the stage (codes, S^-1, operand blocks). */
 
 void twoace_default_params(twoace_params* p);
 
@@ -107,6 +107,14 @@ int twoace_solve_batch(twoace_ctx* ctx, int variant, int mem, int nb, int tx, in
                        const int32_t* m, const double* A, const double* B, const int32_t* train_idx,
                        const twoace_params* params, double* X, double* Y, double* quality,
                        double* info, double* stage_words);
+
+/* Residual trace (the optional fourth output of SURVEY.md section 8b): after twoace_set_trace(ctx, mem, buf, cap) every
+ * twoace_solve_batch / twoace_solve_batch_codebook call also writes, per instance and InferADMM stage, the combined
+ * residual res_comb (inferLowRankV4.m:345) of every executed iteration:
+ *   buf[(b * (4T+1) + stage) * maxiter + (it - 1)],   NaN for iterations / stages that did not run
+ * (stage order as in stage_words).  buf holds `capacity` doubles, host or device per `mem`; device buffers need an
+ * even nb * (4T+1) * maxiter.  twoace_set_trace(ctx, mem, NULL, 0) switches the trace off again. */
+int twoace_set_trace(twoace_ctx* ctx, int mem, double* trace, int64_t capacity);
 
 /* Register a codebook shared by all instances: rows x n complex, column-major (the `cb` variable of
  * codebook/codebook_mat, the .mat files), host or device per `mem`.  Kept on the device until replaced. */
@@ -186,10 +194,15 @@ int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const
  * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass;
  * "dedup_nuclear_rerun" (default 0): inferLowRank_Nuclear.m:69-70 reruns the train solve with use_rank_one = true,
  * a flag its ArgMinZ (:411-419) never reads, so the rerun reproduces the first run bit for bit; 1 = do not
- * re-execute it (identical X, Y, quality, flags; roughly 1.6x fewer iterations when quality < 0.6). */
+ * re-execute it (identical X, Y, quality, flags; roughly 1.6x fewer iterations when quality < 0.6);
+ * "tensor" (default 1): the two sensing-matrix products of the cluster kernel run as exact int8 tensor-core products
+ * (tcgen05, csrc/tc_prod.cuh), 0 = FP64 SIMT products; "cache_sinv" (default 1): the stages of one trial share one
+ * (I + A A')^-1 instead of inverting it once per stage. */
 int twoace_set_option(twoace_ctx* ctx, const char* key, int value);
 /* InferADMM launches that took the shared-memory cluster kernel since context creation. */
 int64_t twoace_fast_launch_count(const twoace_ctx* ctx);
+/* launches of the cluster kernel whose A-products ran as exact int8 tensor-core (tcgen05) products */
+int64_t twoace_tensor_launch_count(const twoace_ctx* ctx);
 
 /* Measurement hooks (bench.py).  With timing on, every InferADMM stage-kernel launch is bracketed by
  * CUDA events on the context's stream; twoace_timing_collect synchronises, returns the summed

@@ -456,9 +456,11 @@ def _older_version(A, B, tx, rx, p: Params, train_idx, info: SolveInfo, profile:
     retry; V1 / V2 skip the refine when quality <= 0.6 (V2.m:47-58), V3 refines either way (V3.m:50-62)."""
     A = np.asarray(A, dtype=np.complex128)
     m, n = A.shape
-    r = min(p.r, m, n)
     A, B, A_norm, B_norm = _preprocess(A, B, p.tol_abs)
     train_idx = np.asarray(train_idx, dtype=np.int64)
+    # the spectral init of these versions runs INSIDE inferLowRankImpl, after r = min([r m n]) has been
+    # re-evaluated with m = m_train (V3.m:198-200, V2.m:193-195, inferLowRank.m:193-195): r <= m_train
+    r = min(p.r, m, n, int(train_idx.size))
     test_idx = test_index_set(m, train_idx)
     A_train, B_train = A[train_idx, :], B[train_idx]
     Xs = spectral_initialize(A_train, B_train, r)            # V3.m:213-224 (inside inferLowRankImpl there)

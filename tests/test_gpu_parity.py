@@ -69,27 +69,24 @@ def test_spectral_init_n_by_n_branch(codebook, gpu_ctx):
     assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-9
 
 
-@pytest.fixture(params=["general", "fast_cs2", "fast_cs4"])
+@pytest.fixture(params=["general", "fast_cs2", "fast_cs4", "simt_cs2", "simt_cs4"])
 def kernel_path(request, gpu_ctx):
-    """Run a test on the general kernel and on the shared-memory cluster kernel (cluster size 2 and 4)."""
+    """Run a test on the general kernel and on the shared-memory cluster kernel: cluster size 2 and 4, with the
+    A-products on the tensor cores (tcgen05 int8, the default) and as FP64 SIMT products ("simt_*")."""
     gpu_ctx.set_option("fast", 0 if request.param == "general" else 1)
-    gpu_ctx.set_option("fast_cs", 4 if request.param == "fast_cs4" else 2)
+    gpu_ctx.set_option("fast_cs", 4 if request.param.endswith("cs4") else 2)
+    gpu_ctx.set_option("tensor", 0 if request.param.startswith("simt") else 1)
     yield request.param
     gpu_ctx.set_option("fast", 1)
     gpu_ctx.set_option("fast_cs", 2)
+    gpu_ctx.set_option("tensor", 1)
 
 
-@pytest.mark.parametrize("sbr,r,r1,nuc", [(True, 20, False, False), (False, 20, False, False),
-                                          (True, 1, True, False), (True, 20, True, False),
-                                          (True, 20, False, True), (False, 20, False, True), (True, 1, False, True),
-                                          (False, 7, False, False)])
-@pytest.mark.parametrize("iters", [1, 2, 10, 100])
-def test_stage_state_parity(codebook, gpu_ctx, kernel_path, sbr, r, r1, nuc, iters):
+def _stage_check(gpu_ctx, At, Bt, X0, sbr, r1, nuc, iters):
+    """One InferADMM call on the GPU against the oracle from the same start point: iterate state, outputs and the
+    integer bookkeeping.  Returns the stage words."""
     import twoace_b200 as tw
     from twoace_b200 import solvers as sv
-    At, Bt = _stage_case(codebook, 64)
-    fast0 = gpu_ctx.fast_launch_count
-    X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
     snap = {iters: None}
     tro = admm.StageTrace()
     zfn = admm.argmin_z_nuclear if nuc else admm.argmin_z
@@ -119,8 +116,48 @@ def test_stage_state_parity(codebook, gpu_ctx, kernel_path, sbr, r, r1, nuc, ite
         assert abs(W[0][0] - tro.mu) <= 1e-12 * tro.mu
         assert int(W[0][3]) == tro.opt_iter and int(W[0][4]) == tro.opt_col     # bit-exact bookkeeping
         assert int(W[0][5]) == tro.n_mu_bumps
+    return W[0]
+
+
+@pytest.mark.parametrize("sbr,r,r1,nuc", [(True, 20, False, False), (False, 20, False, False),
+                                          (True, 1, True, False), (True, 20, True, False),
+                                          (True, 20, False, True), (False, 20, False, True), (True, 1, False, True),
+                                          (False, 7, False, False)])
+@pytest.mark.parametrize("iters", [1, 2, 10, 100])
+def test_stage_state_parity(codebook, gpu_ctx, kernel_path, sbr, r, r1, nuc, iters):
+    At, Bt = _stage_case(codebook, 64)
+    fast0, tc0 = gpu_ctx.fast_launch_count, gpu_ctx.tensor_launch_count
+    X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
+    _stage_check(gpu_ctx, At, Bt, X0, sbr, r1, nuc, iters)
     eligible = kernel_path != "general" and r in (1, 20)
     assert (gpu_ctx.fast_launch_count - fast0 == 1) == eligible      # the intended kernel really ran
+    assert (gpu_ctx.tensor_launch_count - tc0 == 1) == (kernel_path.startswith("fast") and r == 20)
+
+
+@pytest.mark.parametrize("M,snr", [(32, 0.0), (32, 30.0), (128, 0.0), (128, 30.0), (256, 0.0), (256, 30.0)])
+@pytest.mark.parametrize("iters", [1, 2, 10, 100, 320])
+@pytest.mark.parametrize("tensor", [1, 0])
+def test_stage_state_parity_headline_grid(codebook, gpu_ctx, M, snr, iters, tensor):
+    """The operating points of the headline benchmark (inferLowRank_Nuclear, M in {32,128,256}, SNR 0/30 dB) on the
+    kernel each of them takes by default -- cluster size 2 (m = 30) and cluster size 4 (m = 121, 243), with the
+    tensor-core and with the FP64 SIMT products -- up to an iteration count at which the singular-value
+    threshold 1/mu no longer zeroes Z, so that the r x r eigensolve of inferLowRank_Nuclear.m:411-439 is live."""
+    from twoace_b200 import harness as hz
+    ins = hz.make_batch(1, codebook, M, snr)[0]
+    A, B, _, _ = admm._preprocess(ins.A, ins.B, 1e-8)
+    tr = ins.train_idx[0]
+    At, Bt = A[tr], B[tr]
+    X0 = admm.spectral_initialize(At, Bt, 20)
+    gpu_ctx.set_option("tensor", tensor)
+    try:
+        fast0, tc0 = gpu_ctx.fast_launch_count, gpu_ctx.tensor_launch_count
+        W = _stage_check(gpu_ctx, At, Bt, X0, True, False, True, iters)
+        assert gpu_ctx.fast_launch_count - fast0 == 1
+        assert gpu_ctx.tensor_launch_count - tc0 == tensor
+        if iters >= 320:
+            assert W[8] > 0      # Jacobi sweeps were executed: the SVT was live
+    finally:
+        gpu_ctx.set_option("tensor", 1)
 
 
 @pytest.mark.parametrize("M", [36, 121, 225, 361])
@@ -522,3 +559,40 @@ def test_nuclear_rerun_dedup_is_bitwise_identical(codebook, gpu_ctx):
         assert np.array_equal(a, b)
     assert np.array_equal(lit.info[:, :15], ded.info[:, :15], equal_nan=True)
     assert ded.info[:, 15].sum() < lit.info[:, 15].sum()  # fewer iterations executed
+
+
+def test_residual_trace_output(codebook, gpu_ctx):
+    """The optional residual trace (twoace_set_trace): res_comb of every executed iteration of every stage, NaN
+    elsewhere; its last finite entry of a stage is stage word 7 and the count of finite entries the iteration count.
+    Checked against the oracle's per-iteration res_comb for the first stage."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    insts = hz.make_batch(3, codebook, 64, 20.0)
+    p = tw.Params.default()
+    nstage, maxiter = 5, int(p.maxiter)
+    buf = np.zeros(len(insts) * nstage * maxiter, dtype=np.float64)
+    gpu_ctx.set_trace(buf)
+    try:
+        res = sv.solve_batch(tw.V4, [i.A for i in insts], [i.B for i in insts], TX, RX,
+                             [i.train_idx[:1] for i in insts], p, gpu_ctx)
+    finally:
+        gpu_ctx.set_trace(None)
+    tr = buf.reshape(len(insts), nstage, maxiter)
+    for b, ins in enumerate(insts):
+        for st in range(nstage):
+            iters = int(res.stage_words[b][st][2])
+            fin = np.isfinite(tr[b, st])
+            assert fin.sum() == iters and fin[:iters].all()
+            if iters:
+                assert tr[b, st, iters - 1] == res.stage_words[b][st][7]
+        # first stage (over-parameterised, training rows) against the oracle's own residual history
+        A, B, _, _ = admm._preprocess(ins.A, ins.B, 1e-8)
+        t = ins.train_idx[0]
+        X0 = admm.spectral_initialize(A[t], B[t], 20)
+        tro = admm.StageTrace()
+        admm.infer_admm(A[t], B[t], X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 1e-4, 1e-8, 500, None, None,
+                        admm.argmin_z, tro)
+        assert int(res.stage_words[b][0][2]) == tro.iters
+        if hasattr(tro, "res_comb") and len(tro.res_comb):
+            ref = np.asarray(tro.res_comb)
+            assert np.allclose(tr[b, 0, :tro.iters], ref, rtol=1e-6, atol=1e-12)

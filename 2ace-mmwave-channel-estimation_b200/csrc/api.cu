@@ -10,6 +10,7 @@
 
 #include "../../include/twoace.h"
 #include "solve_kernels.cuh"
+#include "big_stage.cuh"
 #include "phaselift.cuh"
 #include "metrics.cuh"
 
@@ -219,6 +220,58 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
   return 0;
 }
 
+// 256 < m <= 1024 on the chunked cluster kernel (big_stage.cuh)
+static int launch_big(twoace_ctx* ctx, const StageTask* dt, int ntasks, const DevParams& prm, FastDims fd, bool* launched) {
+  *launched = false;
+  auto kern = big_stage_kernel;
+  const size_t smem = std::max(fast_smem_bytes<BIG_RL>(fd), (size_t)117 * 1024);
+  if (smem > SMEM_LIMIT) return 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.gridDim = dim3((unsigned)(BIG_CS * ntasks), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = BIG_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int maxcl = 0;
+  CK(cudaOccupancyMaxActiveClusters(&maxcl, kern, &cfg));
+  if (maxcl < 1) return 0;
+  const int ncl = std::max(1, std::min(ntasks, maxcl));
+  fd.ws_stride = (big_ws_elems(fd.mfull) + 15) / 16 * 16;
+  int rc = ensure(ctx, ctx->ws, (size_t)ncl * fd.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  cfg.gridDim = dim3((unsigned)(ncl * BIG_CS), 1, 1);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p));
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+    char lb[160];
+    snprintf(lb, sizeof lb, "big_stage_kernel tasks %d clusters %d mfull %d smem %zu nslot %d n1 %d", ntasks, ncl, fd.mfull,
+             smem, fd.tc.nslot, fd.tc.n1);
+    ctx->stage_labels.emplace_back(lb);
+  }
+  ctx->launches++;
+  ctx->fast_launches++;
+  ctx->tc_launches++;
+  *launched = true;
+  return 0;
+}
+
+static bool big_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
+  return ctx->opt_fast && ctx->opt_tensor && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
+         t.m > 256 && t.m <= BIG_MMAX && t.r == BIG_R && !t.nuclear && (t.rank_one == 0 || t.rank_one == 1);
+}
+
 static bool fast_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
   return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
          t.m <= 256 && (t.r == 20 || t.r == 1) && (!t.nuclear || t.r == 1 || t.m >= 26) &&
@@ -287,11 +340,12 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
                         int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
   // groups: 0 = <10,2> tensor-core, 1 = <5,4> tensor-core, 2 = <10,2> SIMT, 3 = <5,4> SIMT, 4 = r = 1
-  std::vector<StageTask> grp[5], gen;
+  std::vector<StageTask> grp[5], gen, big;
   bool nuc = false;
   for (const StageTask& t : tasks) nuc = nuc || t.nuclear;     // a launch is all-nuclear or all-V4
   const bool tc = ctx->opt_tensor != 0;
   for (const StageTask& t : tasks) {
+    if (big_eligible(ctx, t, n, tx, rx)) { big.push_back(t); continue; }
     if (!fast_eligible(ctx, t, n, tx, rx)) { gen.push_back(t); continue; }
     if (t.r == 1) { grp[4].push_back(t); continue; }
     const bool want2 = ctx->opt_fast_cs == 2;
@@ -332,6 +386,20 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     }
     if (rc) return rc;
     if (!launched) FAIL(TWOACE_E_CUDA, "cluster kernel launch configuration rejected (group %d, maxm %d)", g, fd.maxm);
+  }
+  if (!big.empty()) {
+    std::stable_sort(big.begin(), big.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
+    FastDims fd = {};
+    fd.maxm = BIG_CH; fd.mw = BIG_CH / 16; fd.r = BIG_R; fd.ws_stride = 0; fd.nuclear = 0; fd.ds = 16;
+    fd.mfull = big.front().m;
+    if (!fast_tc_layout<BIG_RL>(fd, SMEM_LIMIT)) FAIL(TWOACE_E_CUDA, "internal: chunked cluster kernel layout (mfull %d)", fd.mfull);
+    const StageTask* dt = nullptr;
+    int rc = upload_tasks(ctx, big, cursor, &dt);
+    if (rc) return rc;
+    bool launched = false;
+    rc = launch_big(ctx, dt, (int)big.size(), prm, fd, &launched);
+    if (rc) return rc;
+    if (!launched) FAIL(TWOACE_E_CUDA, "chunked cluster kernel launch configuration rejected (mfull %d)", fd.mfull);
   }
   return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
 }
@@ -516,9 +584,10 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   const size_t o_codes = (dense && try_codes) ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
   const size_t o_qflag = (dense && try_codes) ? bp.take((size_t)nb * sizeof(int)) : 0;
   // per-instance store of (I + A_train A_train')^-1: the stages of a trial (over-parameterised, refinement and their
-  // rank-one reruns) share the training rows, so only the first of them inverts (instances on the cluster kernel)
+  // rank-one reruns) share the training rows, so only the first of them inverts (instances on the cluster kernels;
+  // m x m Woodbury core for m <= 256, the n x n matrix (A'A + I)^-1 of the chunked kernel above)
   std::vector<size_t> sv_off(nb + 1, 0);
-  for (int b = 0; b < nb; ++b) sv_off[b + 1] = sv_off[b] + ((try_codes && ctx->opt_cache_sinv && mtr[b] <= 256) ? (size_t)mtr[b] * mtr[b] : 0);
+  for (int b = 0; b < nb; ++b) sv_off[b + 1] = sv_off[b] + ((try_codes && ctx->opt_cache_sinv && mtr[b] <= BIG_MMAX) ? (mtr[b] <= 256 ? (size_t)mtr[b] * mtr[b] : (size_t)FN * FN) : 0);
   const size_t o_sinv = sv_off[nb] ? bp.take(sv_off[nb] * sizeof(cd)) : 0;
   int rc = ensure(ctx, ctx->arena, bp.off + 256);
   if (rc) return rc;

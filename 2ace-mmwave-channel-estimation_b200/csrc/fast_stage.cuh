@@ -31,7 +31,8 @@ constexpr int FTX = 16;    // tx (= rx)
 constexpr int XS_SCAL = 16;
 
 struct FastDims {
-  int maxm;          // largest m in the launch
+  int maxm;          // largest m in the launch (big_stage.cuh: rows per chunk)
+  int mfull;         // big_stage.cuh: largest m in the launch (0 otherwise)
   int mw;            // ceil(maxm/16): words per k of the [i-word][k] code copy
   int r;             // total columns (CS * RL)
   int ds;            // shared eig dimension: 16 (V4: tx x tx) or max(16, r) (nuclear: r x r)
@@ -107,7 +108,8 @@ __host__ __device__ inline FastSmem<RL> fast_carve(unsigned char* base, const Fa
   s.js.e = (cd*)take((size_t)h * sizeof(cd), 16);
   s.js.cs = (double*)take((size_t)h * sizeof(double), 8);
   s.js.sn = (double*)take((size_t)h * sizeof(double), 8);
-  s.Bs = (double*)take((size_t)d.maxm * sizeof(double), 8);
+  const size_t mb = (size_t)(d.mfull > d.maxm ? d.mfull : d.maxm);
+  s.Bs = (double*)take(mb * sizeof(double), 8);
   s.xrow = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
   s.rowtot = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
   s.xsc = (double*)take(2 * XS_SCAL * sizeof(double), 8);
@@ -116,7 +118,7 @@ __host__ __device__ inline FastSmem<RL> fast_carve(unsigned char* base, const Fa
   s.s2s = (double*)take(SMALL_DMAX * sizeof(double), 8);
   s.colsc = (double*)take(2 * SMALL_DMAX * sizeof(double), 8);
   s.sc = (double*)take(32 * sizeof(double), 8);
-  s.rows_s = (int*)take((size_t)d.maxm * sizeof(int), 4);
+  s.rows_s = (int*)take(mb * sizeof(int), 4);
   s.ifl = (int*)take(48 * sizeof(int), 4);
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;

@@ -267,6 +267,46 @@ static int launch_big(twoace_ctx* ctx, const StageTask* dt, int ntasks, const De
   return 0;
 }
 
+// r = 1 stages with 256 < m <= 1024 (the refinement on all rows): one CTA per task, two per SM
+static int launch_big1(twoace_ctx* ctx, const StageTask* dt, int ntasks, const DevParams& prm, FastDims fd, bool* launched) {
+  *launched = false;
+  auto kern = big1_stage_kernel;
+  const size_t smem = fast_smem_bytes<1>(fd);
+  if (smem > SMEM_LIMIT) return 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  if (occ < 1) return 0;
+  const int grid = std::max(1, std::min(ntasks, occ * ctx->num_sms));
+  fd.ws_stride = (big1_ws_elems() + 15) / 16 * 16;
+  int rc = ensure(ctx, ctx->ws, (size_t)grid * fd.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  kern<<<grid, NT, smem, ctx->stream>>>(dt, ntasks, prm, fd, (cd*)ctx->ws.p);
+  CK(cudaGetLastError());
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+    char lb[160];
+    snprintf(lb, sizeof lb, "big1_stage_kernel tasks %d grid %d (x%d per SM) maxm %d smem %zu", ntasks, grid, occ, fd.maxm, smem);
+    ctx->stage_labels.emplace_back(lb);
+  }
+  ctx->launches++;
+  ctx->fast_launches++;
+  *launched = true;
+  return 0;
+}
+
+static bool big1_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
+  return ctx->opt_fast && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
+         t.m > 256 && t.m <= BIG_MMAX && t.r == 1 && !t.nuclear && (t.rank_one == 0 || t.rank_one == 1);
+}
+
 static bool big_eligible(const twoace_ctx* ctx, const StageTask& t, int n, int tx, int rx) {
   return ctx->opt_fast && ctx->opt_tensor && t.codes != nullptr && t.cscale != nullptr && n == FN && tx == FTX && rx == FTX &&
          t.m > 256 && t.m <= BIG_MMAX && t.r == BIG_R && !t.nuclear && (t.rank_one == 0 || t.rank_one == 1);
@@ -340,12 +380,13 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
                         int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
   // groups: 0 = <10,2> tensor-core, 1 = <5,4> tensor-core, 2 = <10,2> SIMT, 3 = <5,4> SIMT, 4 = r = 1
-  std::vector<StageTask> grp[5], gen, big;
+  std::vector<StageTask> grp[5], gen, big, big1;
   bool nuc = false;
   for (const StageTask& t : tasks) nuc = nuc || t.nuclear;     // a launch is all-nuclear or all-V4
   const bool tc = ctx->opt_tensor != 0;
   for (const StageTask& t : tasks) {
     if (big_eligible(ctx, t, n, tx, rx)) { big.push_back(t); continue; }
+    if (big1_eligible(ctx, t, n, tx, rx)) { big1.push_back(t); continue; }
     if (!fast_eligible(ctx, t, n, tx, rx)) { gen.push_back(t); continue; }
     if (t.r == 1) { grp[4].push_back(t); continue; }
     const bool want2 = ctx->opt_fast_cs == 2;
@@ -400,6 +441,18 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     rc = launch_big(ctx, dt, (int)big.size(), prm, fd, &launched);
     if (rc) return rc;
     if (!launched) FAIL(TWOACE_E_CUDA, "chunked cluster kernel launch configuration rejected (mfull %d)", fd.mfull);
+  }
+  if (!big1.empty()) {
+    std::stable_sort(big1.begin(), big1.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
+    FastDims fd = {};
+    fd.maxm = big1.front().m; fd.mw = (fd.maxm + 15) / 16; fd.r = 1; fd.ds = 16; fd.lean = 1;
+    const StageTask* dt = nullptr;
+    int rc = upload_tasks(ctx, big1, cursor, &dt);
+    if (rc) return rc;
+    bool launched = false;
+    rc = launch_big1(ctx, dt, (int)big1.size(), prm, fd, &launched);
+    if (rc) return rc;
+    if (!launched) FAIL(TWOACE_E_CUDA, "r = 1 large-m kernel launch configuration rejected (maxm %d)", fd.maxm);
   }
   return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
 }

@@ -584,4 +584,291 @@ big_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm,
   if (threadIdx.x < 32) umma::tmem_free512(tc.tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// r = 1 stages for 256 < m <= 1024: the refinement on all rows (inferLowRankV4.m:68-80).  One CTA per task, two CTAs
+// per SM; the iterate (X, Z, N: 256; Y, M, Y - Y0, A X: m) lives in shared memory, U = (A'A + I)^-1 in L2, the 2-bit
+// codes are read straight from global memory (64 B per row, L1/L2-resident).  Both sensing-matrix products are
+// multiply-free: u in {1, j, -1, -j} turns every term into a swap / negate and two additions.
+
+// acc += j^c v
+__device__ __forceinline__ void cadd_rot(cd& acc, uint32_t c, cd v) {
+  const bool odd = (c & 1u) != 0u;
+  double a = odd ? -v.y : v.x;
+  double b = odd ? v.x : v.y;
+  if (c & 2u) { a = -a; b = -b; }
+  acc.x += a;
+  acc.y += b;
+}
+
+// out(i, sum_k u(i,k) x(k)) for i < m: thread t owns rows t, t + 256, ... (up to four), every x(k) read from shared
+// memory once per thread and used for all of its rows.
+template <class OutF>
+__device__ __forceinline__ void big1_prod_a(const uint32_t* __restrict__ codes, const int* rows_s, int m, const cd* x, OutF out) {
+  const int tid = threadIdx.x;
+  const int nq = (m + NT - 1) / NT;
+  const uint4* cr[4];
+  cd acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + NT * q;
+    cr[q] = reinterpret_cast<const uint4*>(codes + (size_t)rows_s[i < m ? i : 0] * 16);
+    acc[q] = cmk(0.0, 0.0);
+  }
+  for (int w4 = 0; w4 < 4; ++w4) {
+    uint4 cw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cw[q] = (q < nq) ? __ldg(cr[q] + w4) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) {
+      uint32_t wd[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wd[q] = ww == 0 ? cw[q].x : ww == 1 ? cw[q].y : ww == 2 ? cw[q].z : cw[q].w;
+      const cd* xv = x + 64 * w4 + 16 * ww;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const cd v = xv[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) cadd_rot(acc[q], (wd[q] >> (2 * k)) & 3u, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + NT * q;
+    if (i < m) out(i, acc[q]);
+  }
+}
+
+// out(k, sum_i conj(u(i,k)) in(i)) for k < 256.  Warp w owns the code words 2w, 2w + 1 (k in [32 w, 32 w + 32)); its
+// lanes are 16 row subsets x 2 words, lane subset s takes rows s, s + 16, ...; the 16 partial sums of every k are
+// combined by a shuffle reduce-scatter, after which the lane of subset s holds k = 16 word + s.
+template <class InF, class OutF>
+__device__ __forceinline__ void big1_prod_ah(const uint32_t* __restrict__ codes, const int* rows_s, int m, InF in, OutF out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = lane & 15, w = 2 * warp + (lane >> 4);
+  cd acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = cmk(0.0, 0.0);
+  for (int i = s; i < m; i += 16) {
+    const uint32_t wd = __ldg(codes + (size_t)rows_s[i] * 16 + w);
+    const cd t = in(i);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cadd_rot(acc[j], (0u - (wd >> (2 * j))) & 3u, t);      // conj(j^c) = j^(-c)
+  }
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (s & h) != 0;
+#pragma unroll
+    for (int j = 0; j < h; ++j) {
+      const cd mine = up ? acc[j + h] : acc[j];
+      const cd give = up ? acc[j] : acc[j + h];
+      acc[j] = cmk(mine.x + __shfl_xor_sync(0xffffffffu, give.x, h), mine.y + __shfl_xor_sync(0xffffffffu, give.y, h));
+    }
+  }
+  out(16 * w + s, acc[0]);
+}
+
+__device__ inline void run_big1(const StageTask& tk, const DevParams& prm, const FastSmem<1>& sm, cd* wsg) {
+  const int tid = threadIdx.x;
+  const int m = tk.m;
+  const double cs = *tk.cscale, bsc = *tk.bscale;
+  const int rank_one = tk.rank_one_ptr ? *tk.rank_one_ptr : tk.rank_one;
+  const long long ttask0 = clock64();
+  cd* U = wsg;                        // (A'A + I)^-1
+  cd* AtY = wsg + (size_t)FN * FN;    // [256]
+  const uint32_t* codes = tk.codes;
+  for (int i = tid; i < m; i += NT) {
+    sm.rows_s[i] = tk.A.rows ? tk.A.rows[i] : i;
+    sm.Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
+  }
+  jacobi_tables<FTX>(sm.pairs);
+  __syncthreads();
+  double nb2;
+  {
+    double v[1] = {0.0};
+    for (int i = tid; i < m; i += NT) v[0] += sm.Bs[i] * sm.Bs[i];
+    block_sum<1>(v, sm.red);
+    nb2 = v[0];
+  }
+  const double normB = sqrt(nb2);
+  // ---- U = (A'A + I)^-1  (:220-222): column l of A'A is A' u(:, l), exact in FP64 (sums of 1, j, -1, -j)
+  {
+    const double cs2 = cs * cs;
+    for (int l = 0; l < FN; ++l) {
+      const int wl = l >> 4, sh = 2 * (l & 15);
+      big1_prod_ah(codes, sm.rows_s, m,
+                   [&](int i) {
+                     const uint32_t c = (__ldg(codes + (size_t)sm.rows_s[i] * 16 + wl) >> sh) & 3u;
+                     return cmk((double)((c == 0u) - (c == 2u)), (double)((c == 1u) - (c == 3u)));
+                   },
+                   [&](int k, cd v) { U[k + (size_t)FN * l] = cmk(fma(cs2, v.x, k == l ? 1.0 : 0.0), cs2 * v.y); });
+    }
+    __threadfence_block();
+    __syncthreads();
+    spd_inverse(U, FN, sm.WT, sm.WT + FN);
+    __syncthreads();
+  }
+  // ---- X = X0, M = N = 0, rescale so |A X| matches |B| (:278-286), Y = normalize_rows(A X, B) (:287)
+  for (int k = tid; k < FN; k += NT) { sm.X[k] = tk.X0[k]; sm.N[k] = cmk(0.0, 0.0); }
+  for (int i = tid; i < m; i += NT) sm.M[i] = cmk(0.0, 0.0);
+  __syncthreads();
+  big1_prod_a(codes, sm.rows_s, m, sm.X, [&](int i, cd v) { sm.AX[i] = cscale(v, cs); });
+  __syncthreads();
+  {
+    double v[1] = {0.0};
+    for (int i = tid; i < m; i += NT) v[0] += cabs2(sm.AX[i]);
+    block_sum<1>(v, sm.red);
+    const double s = normB / sqrt(v[0]);
+    for (int k = tid; k < FN; k += NT) sm.X[k] = cscale(sm.X[k], s);
+    for (int i = tid; i < m; i += NT) {
+      cd a = cscale(sm.AX[i], s);
+      double D = sqrt(cabs2(a));
+      if (D == 0.0) { a = cmk(1.0, 0.0); D = 1.0; }
+      sm.Y[i] = cscale(a, sm.Bs[i] / D);
+    }
+  }
+  __syncthreads();
+  int sweeps = 0;
+  double nz[4];
+  if (tid == 0) sm.ifl[2] = 0;
+  __syncthreads();
+  fast_argmin_z<1, 1>(m, rank_one, sm, 1.0, true, false, nz, &sweeps);     // Z = ArgMinZ(X, 0, 1)  (:288)
+  __syncthreads();
+  if (prm.need_dual)     // AtY = A' Y  (:289)
+    big1_prod_ah(codes, sm.rows_s, m, [&](int i) { return sm.Y[i]; }, [&](int k, cd v) { AtY[k] = cscale(v, cs); });
+
+  double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
+  int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
+  if (tid == 0) { sm.sc[20] = 0.0; sm.sc[21] = 0.0; sm.sc[22] = 0.0; sm.sc[23] = 0.0; sm.sc[24] = 0.0; }
+  __syncthreads();
+  const long long tl0 = clock64();
+
+  for (int it = 1; it <= prm.maxiter; ++it) {
+    const double imu = 1.0 / mu, i1mu = 1.0 / (1.0 + mu);
+    const long long tx0 = clock64();
+    // ---- X update (:304, :380-388): X = U (A'(Y - M/mu) + Z - N/mu)
+    big1_prod_ah(codes, sm.rows_s, m,
+                 [&](int i) {
+                   const cd y = sm.Y[i], mm = sm.M[i];
+                   return cmk(fma(-mm.x, imu, y.x), fma(-mm.y, imu, y.y));
+                 },
+                 [&](int k, cd v) {
+                   const cd z = sm.Z[k], nn = sm.N[k];
+                   sm.X[k] = cmk(fma(v.x, cs, fma(-nn.x, imu, z.x)), fma(v.y, cs, fma(-nn.y, imu, z.y)));
+                 });
+    __syncthreads();
+    prod_sq_inplace<1>(U, sm.X);
+    const long long tx1 = clock64();
+    if (tid == 0) sm.sc[21] += (double)(tx1 - tx0);
+    // ---- A X (:305), Y update (:308), M update (:315-316), objective (:323-340); Y - Y0 kept in WT for A'(Y - Y0)
+    big1_prod_a(codes, sm.rows_s, m, sm.X, [&](int i, cd v) { sm.AX[i] = cscale(v, cs); });
+    double pYd2 = 0.0, pJM2 = 0.0, pY2 = 0.0, pAX2 = 0.0, obj2 = 0.0;
+    for (int i = tid; i < m; i += NT) {       // every thread touches only the rows it has just written
+      const cd ax = sm.AX[i], mm = sm.M[i], yo = sm.Y[i];
+      cd cc = cmk(fma(mm.x, imu, ax.x), fma(mm.y, imu, ax.y));
+      double D = sqrt(cabs2(cc));
+      if (D == 0.0) { cc = cmk(1.0, 0.0); D = 1.0; }
+      const double f = (sm.Bs[i] / D + mu) * i1mu;
+      const cd yn = cscale(cc, f);
+      const cd jm = cmk(ax.x - yn.x, ax.y - yn.y), dy = cmk(yn.x - yo.x, yn.y - yo.y);
+      sm.Y[i] = yn;
+      sm.M[i] = cmk(fma(mu, jm.x, mm.x), fma(mu, jm.y, mm.y));
+      sm.WT[i] = dy;
+      pYd2 += cabs2(dy); pJM2 += cabs2(jm); pY2 += cabs2(yn);
+      const double a2 = cabs2(ax);
+      pAX2 += a2;
+      const double dd = sqrt(a2) - sm.Bs[i];
+      obj2 += dd * dd;
+    }
+    {
+      double v[5] = {pYd2, pJM2, pY2, pAX2, obj2};
+      block_sum<5>(v, sm.red);
+      pYd2 = v[0]; pJM2 = v[1]; pY2 = v[2]; pAX2 = v[3]; obj2 = v[4];
+    }
+    // ---- A'(Y - Y0) (:309): only feeds res_dual
+    double pAtYd2 = 0.0, pAtY2 = 0.0;
+    if (prm.need_dual) {
+      double v[2] = {0.0, 0.0};
+      big1_prod_ah(codes, sm.rows_s, m, [&](int i) { return sm.WT[i]; },
+                   [&](int k, cd acc) {
+                     const cd d = cscale(acc, cs);
+                     cd a = AtY[k];
+                     a.x += d.x;
+                     a.y += d.y;
+                     AtY[k] = a;
+                     v[0] += cabs2(d);
+                     v[1] += cabs2(a);
+                   });
+      block_sum<2>(v, sm.red);
+      pAtYd2 = v[0]; pAtY2 = v[1];
+    }
+    const long long tx2 = clock64();
+    if (tid == 0) sm.sc[22] += (double)(tx2 - tx1);
+    // ---- Z, N update (:312, :319-320)
+    fast_argmin_z<1, 1>(m, rank_one, sm, mu, false, (sm.ifl[2] & 63) != 0, nz, &sweeps);
+    const long long tx3 = clock64();
+    if (tid == 0) sm.sc[23] += (double)(tx3 - tx2);
+    const double nJN2 = nz[0], nZd2 = nz[1], nX2 = nz[2], nZ2 = nz[3];
+    // ---- best solution so far (:323-340); a NaN objective never wins
+    const double obj = sqrt(obj2);
+    if (obj < opt_obj) {
+      opt_obj = obj; opt_iter = it; opt_col = tk.sbr ? -1 : 0; have_opt = 1;
+      if (tk.Xout) for (int k = tid; k < FN; k += NT) tk.Xout[k] = sm.X[k];
+      if (tk.Yout) for (int i = tid; i < m; i += NT) tk.Yout[i] = sm.Y[i];
+    }
+    // ---- residuals and stopping rule (:343-354)
+    const double res_prim = sqrt(pJM2 + nJN2);
+    const double res_dual = mu * sqrt(pAtYd2 + nZd2);
+    res_comb = sqrt(pJM2 + nJN2 + pYd2 + nZd2);
+    iters = it;
+    if (tk.trace != nullptr && tid == 0) tk.trace[it - 1] = res_comb;
+    if (prm.need_dual) {
+      const double mx1 = fmax(sqrt(pAX2), sqrt(pY2)), mx2 = fmax(sqrt(nX2), sqrt(nZ2));
+      const double th_prim = prm.tol_abs * sqrt((double)(m + FN)) + prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2);
+      const double th_dual = prm.tol_abs * sqrt((double)FN * 2.0) + prm.tol_rel * sqrt(pAtY2 + nZ2);
+      const double th_comb = prm.tol_abs * sqrt((double)(m + FN) * 2.0) + prm.tol_rel * sqrt(mx1 * mx1 + mx2 * mx2 + pY2 + nZ2);
+      if ((res_prim < th_prim && res_dual < th_dual) || (res_comb < th_comb)) { converged = 1; break; }
+    }
+    if (res_comb > last_res * 0.9) { mu *= prm.rho; ++bumps; }   // :358-361
+    last_res = res_comb;
+    __syncthreads();
+    if (tid == 0) sm.sc[24] += (double)(clock64() - tx3);
+  }
+  __syncthreads();
+  if (!have_opt) {    // all-NaN objectives give NaN (H4)
+    if (tk.Xout) for (int k = tid; k < FN; k += NT) tk.Xout[k] = cmk(NAN, NAN);
+    if (tk.Yout) for (int i = tid; i < m; i += NT) tk.Yout[i] = cmk(NAN, NAN);
+  }
+  if (tk.state) {   // [X Z N (n) | Y M (m)]
+    cd* st = tk.state;
+    for (int k = tid; k < FN; k += NT) { st[k] = sm.X[k]; st[FN + k] = sm.Z[k]; st[2 * FN + k] = sm.N[k]; }
+    for (int i = tid; i < m; i += NT) { st[3 * FN + i] = sm.Y[i]; st[3 * FN + m + i] = sm.M[i]; }
+  }
+  if (tk.scal && tid == 0) {
+    tk.scal[SC_MU] = mu; tk.scal[SC_OPT_OBJ] = opt_obj; tk.scal[SC_ITERS] = iters;
+    tk.scal[SC_OPT_ITER] = opt_iter; tk.scal[SC_OPT_COL] = opt_col; tk.scal[SC_BUMPS] = bumps;
+    tk.scal[SC_CONVERGED] = converged; tk.scal[SC_RES_COMB] = res_comb; tk.scal[SC_SWEEPS] = sweeps;
+    tk.scal[9] = sm.sc[20]; tk.scal[10] = sm.sc[21]; tk.scal[11] = (double)(clock64() - tl0);
+    tk.scal[12] = sm.sc[22]; tk.scal[13] = sm.sc[23]; tk.scal[14] = sm.sc[24];
+    tk.scal[15] = (double)(tl0 - ttask0);
+  }
+  __syncthreads();
+}
+
+__host__ __device__ inline size_t big1_ws_elems() { return (size_t)FN * FN + FN; }
+
+__global__ void __launch_bounds__(NT, 2)
+big1_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
+  extern __shared__ __align__(1024) unsigned char big1_smem_raw[];
+  const FastSmem<1> sm = fast_carve<1>(big1_smem_raw, fd);
+  cd* wsg = wsbase + (size_t)blockIdx.x * fd.ws_stride;
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const StageTask tk = tasks[t];
+    if (tk.active != nullptr && *tk.active != tk.active_expect) continue;
+    run_big1(tk, prm, sm, wsg);
+  }
+}
+
 }  // namespace twoace

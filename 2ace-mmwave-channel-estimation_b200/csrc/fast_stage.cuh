@@ -37,6 +37,7 @@ struct FastDims {
   int r;             // total columns (CS * RL)
   int ds;            // shared eig dimension: 16 (V4: tx x tx) or max(16, r) (nuclear: r x r)
   int nuclear;
+  int lean;          // big1_stage_kernel: no code copies, no row-exchange buffers in shared memory
   size_t ws_stride;  // global workspace elements (cd) per cluster
   TcDims tc;         // tensor-core products (tc.on == 0: FP64 SIMT products)
 };
@@ -110,8 +111,8 @@ __host__ __device__ inline FastSmem<RL> fast_carve(unsigned char* base, const Fa
   s.js.sn = (double*)take((size_t)h * sizeof(double), 8);
   const size_t mb = (size_t)(d.mfull > d.maxm ? d.mfull : d.maxm);
   s.Bs = (double*)take(mb * sizeof(double), 8);
-  s.xrow = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
-  s.rowtot = (double*)take((size_t)2 * d.maxm * sizeof(double), 8);
+  s.xrow = (double*)take((size_t)2 * (d.lean ? 16 : d.maxm) * sizeof(double), 8);
+  s.rowtot = (double*)take((size_t)2 * (d.lean ? 16 : d.maxm) * sizeof(double), 8);
   s.xsc = (double*)take(2 * XS_SCAL * sizeof(double), 8);
   s.xcol = (double*)take(2 * SMALL_DMAX * sizeof(double), 8);
   s.red = (double*)take(16 * NW * sizeof(double), 8);
@@ -123,7 +124,10 @@ __host__ __device__ inline FastSmem<RL> fast_carve(unsigned char* base, const Fa
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;
   const size_t cik_bytes = (size_t)16 * d.maxm * 4;
-  if (d.tc.on) {
+  if (d.lean) {
+    s.cki = nullptr; s.cik = nullptr;
+    s.tc_bs = nullptr; s.tc_ex = nullptr; s.tc_bars = nullptr; s.tc_tslot = nullptr;
+  } else if (d.tc.on) {
     s.cki = nullptr;
     s.tc_bs = take(cik_bytes > (size_t)TC_BS_BYTES ? cik_bytes : (size_t)TC_BS_BYTES, 128);
     s.cik = (uint32_t*)s.tc_bs;

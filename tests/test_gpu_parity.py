@@ -96,8 +96,10 @@ def _stage_check(gpu_ctx, At, Bt, X0, sbr, r1, nuc, iters):
     Xg, Yg, Sg, W = sv.infer_admm_batch([At], [Bt], [X0], sbr, r1, TX, RX, p, nuclear=nuc, ctx=gpu_ctx)
     s = snap[iters]
     tol = 1e-9
-    if nuc and iters >= 100:
-        # the nuclear iteration is expansive while tau = 1/mu still zeroes Z (x1.26 per iteration measured):
+    if (nuc and iters >= 100) or (iters >= 60 and At.shape[0] > 256):
+        # the nuclear iteration is expansive while tau = 1/mu still zeroes Z (x1.26 per iteration measured), and so is
+        # the iteration from a raw spectral start at large m (column-wise projection, r = 1: 1e-15 -> 1e-8 ... 1e-3
+        # after 60 iterations in the oracle itself, profiles/r02_big_check_M361_529_1024.log):
         # bound the deviation by the oracle's own response to a 1e-15 relative perturbation of X0
         snap2 = {iters: None}
         rng = np.random.default_rng(1)
@@ -177,6 +179,39 @@ def test_stage_parity_other_shapes(codebook, gpu_ctx, kernel_path, M):
         assert rel(Sg[0]["Y"], snap[iters]["Y"]) < 1e-9
 
 
+@pytest.mark.parametrize("M", [361, 529, 1024])
+@pytest.mark.parametrize("sbr,r,r1", [(True, 20, False), (False, 20, False), (True, 20, True), (True, 1, False),
+                                      (True, 1, True), (False, 1, False)])
+@pytest.mark.parametrize("iters", [1, 10, 60])
+def test_stage_state_parity_large_m(codebook, gpu_ctx, M, sbr, r, r1, iters):
+    """256 < m <= 1024 rows -- the upper half of the reference's M sweep (A2only.m:106-118), where the solver recovers
+    the channel -- on the chunked cluster kernel (r = 20: big_stage_kernel) and the r = 1 refinement kernel
+    (big1_stage_kernel), against the oracle from the same start point."""
+    At, Bt = _stage_case(codebook, M)
+    assert At.shape[0] > 256
+    fast0 = gpu_ctx.fast_launch_count
+    X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
+    _stage_check(gpu_ctx, At, Bt, X0, sbr, r1, False, iters)
+    assert gpu_ctx.fast_launch_count - fast0 == 1      # not the general kernel
+
+
+def test_stage_large_m_convergence_mode(codebook, gpu_ctx):
+    """Default tolerances at m > 256: iteration count, convergence flag and result against the oracle (r = 20 and 1)."""
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    At, Bt = _stage_case(codebook, 529)
+    for r in (20, 1):
+        X0 = admm.spectral_initialize(At, Bt, 20)[:, :r]
+        tro = admm.StageTrace()
+        Xo, Yo, conv = admm.infer_admm(At, Bt, X0, True, False, TX, RX, 0.0, 1e-3, 1.03, 1e-4, 1e-8, 500, None, None,
+                                       admm.argmin_z, tro)
+        fast0 = gpu_ctx.fast_launch_count
+        Xg, Yg, _, W = sv.infer_admm_batch([At], [Bt], [X0], True, False, TX, RX, tw.Params.default(), ctx=gpu_ctx)
+        assert gpu_ctx.fast_launch_count - fast0 == 1
+        assert int(W[0][2]) == tro.iters and bool(W[0][6]) == conv
+        assert rel(Xg[0], Xo) < 1e-9 and rel(Yg[0], Yo) < 1e-9
+
+
 def test_convergence_test_mode_matches_iteration_count(codebook, gpu_ctx, kernel_path):
     import twoace_b200 as tw
     from twoace_b200 import solvers as sv
@@ -221,10 +256,13 @@ def _check_full(res, out, insts, frac=0.95, min_determined=1):
     print(f"\n  reference-determined instances: {det.sum()}/{len(insts)}; gpu-vs-oracle {errs}; oracle self-sensitivity {selfs}")
     assert det.sum() >= min_determined, f"test set has only {det.sum()} reference-determined instances"
     ok = errs <= 1e-4
-    assert ok[det].mean() >= frac, f"only {ok[det].mean():.2%} of the determined instances within 1e-4: {errs} {selfs}"
-    # where the reference is noise-decided (self-sensitivity > 1e-6) both numbers are single samples of a
-    # heavy-tailed, chaotically amplified quantity: no per-instance bound is meaningful there; the instances
-    # still enter the NMSE statistics below and must be finite
+    if det.any():
+        assert ok[det].mean() >= frac, f"only {ok[det].mean():.2%} of the determined instances within 1e-4: {errs} {selfs}"
+    # where the reference is noise-decided (self-sensitivity > 1e-6) both numbers are single samples of a chaotically
+    # amplified quantity: the GPU's deviation from the oracle is held to 100x the oracle's own response to a 1e-14
+    # perturbation of its input; the instances still enter the NMSE statistics below
+    nd = ~det
+    assert np.all(errs[nd] <= np.maximum(1e-4, 100.0 * selfs[nd])), f"noise-decided instances beyond 100x the oracle's self-sensitivity: {errs} {selfs}"
     assert np.all(np.isfinite(res.X) | np.isnan(res.X).all(axis=1, keepdims=True))
     for b in np.nonzero(ok & det)[0]:
         Xo, Yo, qo, info, _ = out[b]
@@ -234,9 +272,10 @@ def _check_full(res, out, insts, frac=0.95, min_determined=1):
         assert int(res.info[b, 4]) == info.best_trial
         assert res.Y[b].shape == Yo.shape
     idx = np.nonzero(det)[0]
-    nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in idx])
-    nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in idx])
-    assert abs(nm_g - nm_o) <= 0.05, (nm_g, nm_o)
+    if len(idx):
+        nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in idx])
+        nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in idx])
+        assert abs(nm_g - nm_o) <= 0.05, (nm_g, nm_o)
     nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in range(len(insts))])
     nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in range(len(insts))])
     assert abs(nm_g - nm_o) <= 1.0, (nm_g, nm_o)
@@ -254,6 +293,29 @@ def test_full_solve_parity_default_tolerances(codebook, gpu_ctx, kernel_path, va
     insts = hz.make_batch(n_inst, codebook, M, snr)
     res, out = _solve_both(variant, insts, tw.Params.default(), admm.Params(), gpu_ctx)
     _check_full(res, out, insts, min_determined=0 if variant_name == "NUCLEAR" else 1)
+
+
+@pytest.mark.parametrize("variant_name,M,n_inst", [("V4", 361, 6), ("V4", 529, 6), ("V4_MULTI", 529, 4), ("V4", 1024, 3)])
+def test_full_solve_parity_where_recovery_works(codebook, gpu_ctx, variant_name, M, n_inst):
+    """M >= 361 at 20 dB is the regime in which the reference recovers the channel (NMSE about -15 dB at M=529), so
+    the parity statistic discriminates here: per-instance error on the reference-determined instances, NMSE of
+    both sides against the true channel, bit-exact flags.  Runs on the large-m cluster kernels."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz
+    variant = getattr(tw, variant_name)
+    insts = hz.make_batch(n_inst, codebook, M, 20.0)
+    fast0 = gpu_ctx.fast_launch_count
+    res, out = _solve_both(variant, insts, tw.Params.default(), admm.Params(), gpu_ctx)
+    assert gpu_ctx.fast_launch_count > fast0
+    # measured (B200, r02): even here the oracle's own CSI moves by 1e-5 ... 2e-1 under a 1e-14 perturbation of the RSS
+    # input (the refinement stages do not converge within 500 iterations), so no instance is reference-determined;
+    # the bar is the 100x-self-sensitivity bound per instance plus the NMSE of both sides against the true channel
+    errs = _check_full(res, out, insts, min_determined=0)
+    nm_g = hz.nmse_db([hz.nmse(res.X[b], insts[b].vecH) for b in range(n_inst)])
+    nm_o = hz.nmse_db([hz.nmse(out[b][0], insts[b].vecH) for b in range(n_inst)])
+    print(f"  M={M} {variant_name}: NMSE gpu {nm_g:.3f} dB, oracle {nm_o:.3f} dB, max err {errs.max():.2e}")
+    if M >= 529:
+        assert nm_o < -8.0 and nm_g < -8.0       # the channel really is recovered on both sides
 
 
 def test_known_answer_nuclear_and_fixed_iterations(gpu_ctx):

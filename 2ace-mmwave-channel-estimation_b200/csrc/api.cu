@@ -13,6 +13,7 @@
 #include "big_stage.cuh"
 #include "phaselift.cuh"
 #include "metrics.cuh"
+#include "synth.cuh"
 
 using namespace twoace;
 
@@ -1333,6 +1334,82 @@ extern "C" int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, in
   ctx->launches++;
   rc = host_back(ctx, mem, out, dO, (size_t)nb * MET_WORDS * sizeof(double)); if (rc) return rc;
   if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" void twoace_synth_default_params(twoace_synth_params* p, int nt, int nr) {
+  p->nt = nt; p->nr = nr; p->L = 3; p->searching_area = 95.0; p->wavelength = 3e8 / 60.48e9; p->spacing = 3.055e-3;
+  p->row_scale = 1.0 / std::sqrt((double)nt * nr); p->cc_frac = 0.95; p->ntrain = 1; p->seed = 58659179ull;
+}
+
+extern "C" int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_params* sp, const int32_t* m,
+                                  const double* snr_db, const int32_t* row_lo, const int32_t* row_hi,
+                                  const int64_t* trial_id, int32_t* cb_rows, int32_t* train_idx, double* B,
+                                  double* vecH, double* angles) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !sp || !m || !snr_db || !row_lo || !row_hi || !trial_id || !cb_rows || !train_idx || !B || !vecH)
+    FAIL(TWOACE_E_INVALID, "null argument");
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  if (!ctx->cb_rm) FAIL(TWOACE_E_INVALID, "no codebook registered (twoace_set_codebook)");
+  const int n = sp->nt * sp->nr;
+  if (sp->nt < 1 || sp->nr < 1 || n != ctx->cb_n) FAIL(TWOACE_E_INVALID, "codebook has n = %d, synthesis asks for nt*nr = %d", ctx->cb_n, n);
+  if (sp->L < 1 || sp->L > 32) FAIL(TWOACE_E_INVALID, "L must be in [1,32]");
+  if (sp->ntrain < 1 || sp->ntrain > 8) FAIL(TWOACE_E_INVALID, "ntrain must be in [1,8]");
+  if (!(sp->cc_frac > 0.0 && sp->cc_frac < 1.0)) FAIL(TWOACE_E_INVALID, "cc_frac must be in (0,1)");
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<size_t> b_off(nb + 1, 0), t_off(nb + 1, 0);
+  int pmax = 2;
+  for (int b = 0; b < nb; ++b) {
+    const int R = row_hi[b] - row_lo[b];
+    if (row_lo[b] < 0 || row_hi[b] > ctx->cb_rows || R < 1) FAIL(TWOACE_E_INVALID, "instance %d: row range [%d,%d) outside the codebook", b, row_lo[b], row_hi[b]);
+    if (m[b] < 2 || m[b] > R) FAIL(TWOACE_E_INVALID, "instance %d: m = %d probes from %d candidate rows", b, m[b], R);
+    if (R > 8192) FAIL(TWOACE_E_UNSUPPORTED, "instance %d: more than 8192 candidate rows", b);
+    while (pmax < R) pmax <<= 1;
+    const int mtr = (int)std::floor((double)m[b] * sp->cc_frac);
+    b_off[b + 1] = b_off[b] + m[b];
+    t_off[b + 1] = t_off[b] + (size_t)sp->ntrain * mtr;
+  }
+  Bump bp;
+  const size_t o_rows = bp.take(b_off[nb] * 4), o_train = bp.take(t_off[nb] * 4), o_tasks = bp.take((size_t)nb * sizeof(SynthTask));
+  int rc = ensure(ctx, ctx->arena, bp.off + 256);
+  if (rc) return rc;
+  char* base = (char*)ctx->arena.p;
+  Staging st;
+  void *dB = nullptr, *dH = nullptr, *dAng = nullptr;
+  rc = dev_out(ctx, st, mem, B, b_off[nb] * sizeof(double), &dB); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, vecH, (size_t)nb * n * sizeof(cd), &dH); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, angles, (size_t)nb * 2 * sp->L * sizeof(double), &dAng); if (rc) return rc;
+  std::vector<SynthTask> tasks(nb);
+  for (int b = 0; b < nb; ++b) {
+    SynthTask& t = tasks[b];
+    t.m = m[b]; t.row_lo = row_lo[b]; t.row_hi = row_hi[b]; t.snr_db = snr_db[b];
+    t.trial = (unsigned long long)trial_id[b];
+    t.rows_out = (int*)(base + o_rows) + b_off[b];
+    t.train_out = (int*)(base + o_train) + t_off[b];
+    t.B_out = (double*)dB + b_off[b];
+    t.vecH_out = (cd*)dH + (size_t)b * n;
+    t.angles_out = dAng ? (double*)dAng + (size_t)b * 2 * sp->L : nullptr;
+  }
+  CK(cudaMemcpyAsync(base + o_tasks, tasks.data(), (size_t)nb * sizeof(SynthTask), cudaMemcpyHostToDevice, ctx->stream));
+  SynthDims dm = {};
+  dm.nt = sp->nt; dm.nr = sp->nr; dm.L = sp->L; dm.ntrain = sp->ntrain;
+  dm.area = sp->searching_area; dm.k_phase = 2.0 * 3.14159265358979323846 / sp->wavelength * sp->spacing;
+  dm.cc_frac = sp->cc_frac; dm.row_scale = sp->row_scale;
+  dm.key0 = (unsigned int)(sp->seed & 0xffffffffull); dm.key1 = (unsigned int)(sp->seed >> 32);
+  dm.pmax = pmax;
+  const size_t smem = synth_smem_bytes(dm);
+  CK(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  synth_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, smem, ctx->stream>>>((const SynthTask*)(base + o_tasks), nb, dm, ctx->cb_rm, n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(cb_rows, base + o_rows, b_off[nb] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(train_idx, base + o_train, t_off[nb] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = host_back(ctx, mem, B, dB, b_off[nb] * sizeof(double)); if (rc) return rc;
+  rc = host_back(ctx, mem, vecH, dH, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
+  rc = host_back(ctx, mem, angles, dAng, (size_t)nb * 2 * sp->L * sizeof(double)); if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));   // the index lists are host outputs
   return TWOACE_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "twoace_set_codebook", "twoace_solve_batch_codebook", "twoace_infer_admm_batch",
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
     "twoace_set_option", "twoace_fast_launch_count", "twoace_tensor_launch_count", "twoace_set_trace", "twoace_pl_default_opts", "twoace_phaselift_batch",
-    "twoace_metrics_batch",
+    "twoace_metrics_batch", "twoace_synth_default_params", "twoace_synth_batch",
 ]
 
 
@@ -66,6 +66,22 @@ class PlOpts(C.Structure):
                 raise TypeError(f"unknown PhaseLift option {k!r}")
             setattr(o, k, v)
         return o
+
+
+class SynthParams(C.Structure):
+    """twoace_synth_params: the numerical-simulation instance generator (Generate_Channel.m, Generate_Measurement.m)."""
+    _fields_ = [("nt", C.c_int32), ("nr", C.c_int32), ("L", C.c_int32), ("searching_area", C.c_double),
+                ("wavelength", C.c_double), ("spacing", C.c_double), ("row_scale", C.c_double),
+                ("cc_frac", C.c_double), ("ntrain", C.c_int32), ("seed", C.c_uint64)]
+
+    @classmethod
+    def default(cls, nt: int = 16, nr: int = 16, **kw) -> "SynthParams":
+        p = cls(nt, nr, 3, 95.0, 3e8 / 60.48e9, 3.055e-3, 1.0 / (nt * nr) ** 0.5, 0.95, 1, 58659179)
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown synthesis parameter {k!r}")
+            setattr(p, k, v)
+        return p
 
 
 class TwoaceError(RuntimeError):
@@ -134,6 +150,11 @@ def load() -> C.CDLL:
     lib.twoace_phaselift_batch.restype = C.c_int
     lib.twoace_metrics_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]
     lib.twoace_metrics_batch.restype = C.c_int
+    lib.twoace_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int, C.c_int]
+    lib.twoace_synth_default_params.restype = None
+    lib.twoace_synth_batch.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SynthParams), i32p, dp, i32p, i32p, vp, i32p, i32p,
+                                       dp, dp, dp]
+    lib.twoace_synth_batch.restype = C.c_int
     _lib = lib
     return lib
 
@@ -257,6 +278,11 @@ class Context:
     def metrics_batch_raw(self, mem, nb, tx, rx, X_est, X_true, phase_bit, out):
         self.check(self.lib.twoace_metrics_batch(self.h, mem, nb, tx, rx, _ptr(X_est), _ptr(X_true), int(phase_bit),
                                                  _ptr(out)))
+
+    def synth_batch_raw(self, mem, nb, sp, m, snr_db, row_lo, row_hi, trial_id, cb_rows, train_idx, B, vecH, angles=None):
+        self.check(self.lib.twoace_synth_batch(self.h, mem, nb, C.byref(sp), _ptr(m), _ptr(snr_db), _ptr(row_lo),
+                                               _ptr(row_hi), _ptr(trial_id), _ptr(cb_rows), _ptr(train_idx), _ptr(B),
+                                               _ptr(vecH), _ptr(angles)))
 
     def spectral_init_batch_raw(self, mem, nb, n, m, A, B, r, Xs):
         self.check(self.lib.twoace_spectral_init_batch(self.h, mem, nb, n, _ptr(m), _ptr(A), _ptr(B), r, _ptr(Xs)))

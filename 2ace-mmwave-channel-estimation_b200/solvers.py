@@ -223,6 +223,31 @@ def evaluation_batch(X_est, X_true, tx: int, rx: int, phase_bit: int = 2, ctx: _
 
 
 # ----------------------------------------------------------------------------- MATLAB-signature calls
+def synth_batch(m, snr_db, row_lo, row_hi, trial_id, sp: "_lib.SynthParams | None" = None,
+                ctx: _lib.Context | None = None):
+    """Instances of the numerical-simulation workload built on the GPU from the registered codebook
+    (twoace_synth_batch: Generate_Channel.m:76-139, A2only.m:137, Generate_Measurement.m:84-101, inferLowRankV4.m:36-37).
+    Returns per-instance lists: rows, train_idx [ntrain, k], B, vecH and the angles [nb, 2L]."""
+    ctx = ctx or _lib.default_context()
+    sp = sp or _lib.SynthParams.default()
+    m = np.ascontiguousarray(np.asarray(m, dtype=np.int32))
+    nb, n = len(m), sp.nt * sp.nr
+    bc = lambda v, dt: np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=dt), (nb,)))
+    snr, lo, hi, tid = bc(snr_db, np.float64), bc(row_lo, np.int32), bc(row_hi, np.int32), bc(trial_id, np.int64)
+    mtr = np.floor(m * sp.cc_frac).astype(np.int64)
+    rows = np.empty(int(m.sum()), np.int32)
+    train = np.empty(int((mtr * sp.ntrain).sum()), np.int32)
+    B = np.empty(int(m.sum()), np.float64)
+    vecH = np.empty(nb * n, np.complex128)
+    ang = np.empty(nb * 2 * sp.L, np.float64)
+    ctx.synth_batch_raw(_lib.MEM_HOST, nb, sp, m, snr, lo, hi, tid, rows, train, B, vecH, ang)
+    bo = np.concatenate([[0], np.cumsum(m)])
+    to = np.concatenate([[0], np.cumsum(mtr * sp.ntrain)])
+    return dict(rows=[rows[bo[b]:bo[b + 1]] for b in range(nb)],
+                train_idx=[train[to[b]:to[b + 1]].reshape(sp.ntrain, -1) for b in range(nb)],
+                B=[B[bo[b]:bo[b + 1]] for b in range(nb)], vecH=vecH.reshape(nb, n), angles=ang.reshape(nb, 2 * sp.L))
+
+
 def MyPhaseLift(measurements, measurementMat, *, opts: PlOpts | None = None, ctx=None):
     """recoveredSig = MyPhaseLift(measurements, measurementMat)   (MyPhaseLift.m:69)."""
     sig, _ = phaselift_batch([np.asarray(measurementMat, np.complex128)], [np.asarray(measurements).reshape(-1)],

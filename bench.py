@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """bench.py — ADMM CSI solves/sec (16x16 antennas, fixed iterations) on N B200s, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config0|config3|config5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload config1|config0|config3|config4|config5] [--dense]
 
 A "step" is one pass of the hot path over one batch of synthetic instances (the same batch every
 step; dense inputs of a batch exceed the 126 MB L2).  Workloads (BASELINE.json configs):
   config1 (default)  inferLowRank_Nuclear, M in {32,64,128,256} x SNR in {0,10,20,30} dB
   config0            inferLowRankV4_multi (what A2only dispatches to), M=64, SNR 20 dB
   config3            MyPhaseLift (TFOCS trace-LS, MyPhaseLift.m defaults: maxIts 4000, tol 1e-10), M=128, 20 dB
+  config4            multiresolution 2ACE: inferLowRankV4_multi, M in [4 36 121 225 361 529 784 1024] with the rows of
+                     every M drawn from its resolution stage of the multires codebook, SNR 20 dB
   config5            inferLowRankV4_multi on 32x32 antennas (n = 1024, general kernel), synthetic 2-bit codebook
+The ADMM workloads on 16x16 antennas run in codebook mode, the way the reference's entry points build A (rows of the
+codebook .mat, A2only.m:137-138): the codebook is registered once, a step's inputs are the row ids, the RSS
+amplitudes and the train splits.  --dense ships a dense complex128 A per instance instead (the round-1 measurement).
 Fixed-iteration mode (ADMM workloads): tol_rel = tol_abs = 0, maxiter = 500.
 N>1: launched under torchrun, one rank per GPU, trials sharded (weak scaling), max-over-ranks time,
 one NCCL all-reduce of the NMSE statistics tensor after the timed region.
@@ -40,6 +46,10 @@ WORKLOADS = {
                     desc="config3: MyPhaseLift (TFOCS AT, maxIts 4000, tol 1e-10, restart 200, lambda 0.05), 16x16, "
                          "M=128, SNR 20 dB"),
 }
+WORKLOADS["config4"] = dict(variant="V4_MULTI", Ms=[4, 36, 121, 225, 361, 529, 784, 1024], snrs=[20.0],
+                            codebook="random_probe_cb_16x16_multires", multires=True,
+                            desc="config4: multiresolution 2ACE, inferLowRankV4_multi, 16x16, M in [4 36 121 225 361 529 "
+                                 "784 1024] (rows of each M from its resolution stage of the multires codebook), SNR 20 dB")
 WORKLOADS["config5"] = dict(variant="V4_MULTI", Ms=[190], snrs=[20.0], tx=32, rx=32,
                             desc="config5: inferLowRankV4_multi, 32x32 antennas (n = 1024), synthetic 2-bit random "
                                  "codebook (Generate_random_beam.m:31-34; none is shipped), M=190, SNR 20 dB")
@@ -52,18 +62,23 @@ def build_instances(wl, trials_per_cell, first_trial):
     from twoace_b200 import harness as hz
     tx, rx = wl.get("tx", 16), wl.get("rx", 16)
     if (tx, rx) == (16, 16):
-        cb = hz.load_codebook()
+        cb = hz.load_codebook(wl.get("codebook", "random_probe_cb_16x16"))
     else:   # no codebook is shipped for other array sizes: 2-bit random beams, fixed seed
         cb = hz._ROOTS[hz.random_beam_codes(np.random.default_rng(20231017), 4096, tx * rx)]
     insts, cells = [], []
     ci = 0
     for M in wl["Ms"]:
         for snr in wl["snrs"]:
+            kw = {}
+            if wl.get("multires"):
+                from twoace_b200.entrypoints import multires_row_range
+                kw["row_range"] = multires_row_range(M)
             batch = hz.make_batch(trials_per_cell, cb, M, snr, base_seed=hz.BASE_SEED + 7919 * ci,
-                                  first_trial=first_trial, Nt=tx, Nr=rx)
+                                  first_trial=first_trial, Nt=tx, Nr=rx, **kw)
             insts += batch
             cells += [ci] * trials_per_cell
             ci += 1
+    wl["_cb"] = cb
     return insts, np.array(cells), ci
 
 
@@ -106,21 +121,24 @@ def _oracle_worker(job):
         else:
             X, _, _ = admm.infer_low_rank_v4(A, B, TX, RX, p, train_idx=train_idx[0])
         dt = time.perf_counter() - t0
-    return X, dt
+    return X, dt, (job[5] if len(job) > 5 else -1)
 
 
 def run_oracle_pool(variant, insts, cores, dims=(16, 16)):
     """Time the NumPy oracle on `insts`, trial-parallel over `cores` single-threaded processes
     (the analogue of the reference's parfor, Vs_M_par.m:145).  Returns (X list, wall seconds)."""
     import multiprocessing as mp
-    jobs = [(variant, i.A, i.B, i.train_idx, dims) for i in insts]
+    order = sorted(range(len(insts)), key=lambda k: -len(insts[k].B))      # longest first
+    jobs = [(variant, insts[k].A, insts[k].B, insts[k].train_idx, dims, k) for k in order]
     ctx = mp.get_context("spawn")
+    out = [None] * len(insts)
     with ctx.Pool(cores) as pool:
         pool.map(_noop, range(cores))            # start the workers (imports) outside the timed region
         t0 = time.perf_counter()
-        out = pool.map(_oracle_worker, jobs, chunksize=1)
+        for X, _, k in pool.imap_unordered(_oracle_worker, jobs, chunksize=1):
+            out[k] = X
         wall = time.perf_counter() - t0
-    return [o[0] for o in out], wall
+    return out, wall
 
 
 def _noop(_):
@@ -188,25 +206,30 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------- main arms
 def reference_arm(args, wl, rank, world):
+    """The reference's CPU path (NumPy oracle: MATLAB / Octave are absent) on all host cores.  A step = 2 x cores solves
+    cycling through the workload's (M, SNR) cells, handed to the workers longest first and one at a time, so that the
+    step time is the throughput of a saturated trial-parallel pool (parfor, Vs_M_par.m:145), not its slowest job."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n_cells = len(wl["Ms"]) * len(wl["snrs"])
-    insts, cells, n_cells = build_instances(wl, max(1, math.ceil(cores / n_cells)), 0)
-    insts = [insts[i] for i in np.argsort(np.arange(len(insts)) % max(1, len(insts) // n_cells), kind="stable")]
-    per_step = max(1, min(len(insts), cores))
-    # a bounded sample per step: `per_step` instances cycling through the (M, SNR) cells
-    order = [insts[i % len(insts)] for i in range(per_step * (args.steps + args.warmup))]
+    per_step = 2 * cores
+    nsteps = args.steps + args.warmup
+    tpc = max(1, math.ceil(per_step * nsteps / n_cells))
+    insts, cells, n_cells = build_instances(wl, tpc, 0)
+    # interleave the cells: instance j of the stream is trial j // n_cells of cell j % n_cells
+    order = [insts[(j % n_cells) * tpc + (j // n_cells) % tpc] for j in range(per_step * nsteps)]
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     times = []
     with ctx.Pool(cores) as pool:
         pool.map(_noop, range(cores))
-        for s in range(args.warmup + args.steps):
-            jobs = [(wl["variant"], i.A, i.B, i.train_idx, (wl.get("tx", 16), wl.get("rx", 16)))
-                    for i in order[s * per_step:(s + 1) * per_step]]
+        for s in range(nsteps):
+            chunk = sorted(order[s * per_step:(s + 1) * per_step], key=lambda i: -len(i.B))
+            jobs = [(wl["variant"], i.A, i.B, i.train_idx, (wl.get("tx", 16), wl.get("rx", 16))) for i in chunk]
             t0 = time.perf_counter()
-            pool.map(_oracle_worker, jobs, chunksize=1)
+            for _ in pool.imap_unordered(_oracle_worker, jobs, chunksize=1):
+                pass
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
@@ -216,9 +239,10 @@ def reference_arm(args, wl, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step": per_step,
-                       "note": "NumPy oracle (port of the MATLAB path; MATLAB/Octave absent), one process per core"},
+                       "note": "NumPy oracle (port of the MATLAB path; MATLAB/Octave absent), one process per core, "
+                               "jobs dispatched longest first"},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} solves per step cycling through the workload's (M,SNR) cells"},
+                             "sample": f"{per_step} solves per step (2 per core) cycling through the workload's (M,SNR) cells"},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -250,14 +274,22 @@ def ours_arm(args, wl, rank, local_rank, world):
     p = tw.Params.default().fixed_iters()
 
     m = np.array([len(i.B) for i in insts], dtype=np.int32)
-    A_h = np.concatenate([i.A.reshape(-1, order="F") for i in insts])
+    dense = bool(args.dense) or N != 256
     B_h = np.concatenate([i.B for i in insts])
     tr_h = np.ascontiguousarray(np.concatenate([i.train_idx[:T].reshape(-1) for i in insts]).astype(np.int32))
     sum_m = int(m.sum())
     nstage = 4 * T + 1
+    row_scale = 1.0 / math.sqrt(N)
+    if dense:
+        A_h = np.concatenate([i.A.reshape(-1, order="F") for i in insts])
+        A_d = torch.from_numpy(A_h.view(np.float64)).to(dev)
+        rows_h = None
+    else:   # codebook mode: the codebook is registered once (like the .mat file the entry points load)
+        ctx.set_codebook(wl["_cb"])
+        rows_h = np.ascontiguousarray(np.concatenate([i.rows for i in insts]).astype(np.int32))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # L2 flush between steps (126 MB L2)
 
     # ---- device-resident inputs/outputs (the `value` leg)
-    A_d = torch.from_numpy(A_h.view(np.float64)).to(dev)
     B_d = torch.from_numpy(B_h).to(dev)
     X_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
     Y_d = torch.empty(sum_m * 2, dtype=torch.float64, device=dev)
@@ -266,11 +298,18 @@ def ours_arm(args, wl, rank, local_rank, world):
     sw_d = torch.empty(nb * nstage * tw.lib.STAGE_WORDS, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
-    def step_device():
-        ctx.solve_batch_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, A_d.data_ptr(), B_d.data_ptr(), tr_h, p,
-                            X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), sw_d.data_ptr())
-
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_device():
+        if dense:
+            ctx.solve_batch_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, A_d.data_ptr(), B_d.data_ptr(), tr_h, p,
+                                X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), sw_d.data_ptr())
+        else:
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, rows_h, row_scale, B_d.data_ptr(),
+                                         tr_h, p, X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(),
+                                         sw_d.data_ptr())
 
     def barrier():
         if world > 1:
@@ -330,16 +369,20 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "flops_per_step": flops_step}
 
     # ---- end to end through the public C ABI with pinned HOST buffers (H2D + D2H inside the region)
-    A_p = torch.from_numpy(A_h.view(np.float64)).pin_memory()
+    A_p = torch.from_numpy(A_h.view(np.float64)).pin_memory() if dense else None
     B_p = torch.from_numpy(B_h).pin_memory()
     X_p = torch.empty(nb * N * 2, dtype=torch.float64).pin_memory()
     Y_p = torch.empty(sum_m * 2, dtype=torch.float64).pin_memory()
     q_p = torch.empty(nb, dtype=torch.float64).pin_memory()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
 
     def step_host():
-        ctx.solve_batch_raw(variant, tw.lib.MEM_HOST, nb, TX, RX, m, A_p.numpy(), B_p.numpy(), tr_h, p,
-                            X_p.numpy(), Y_p.numpy(), q_p.numpy(), None, None)
+        if dense:
+            ctx.solve_batch_raw(variant, tw.lib.MEM_HOST, nb, TX, RX, m, A_p.numpy(), B_p.numpy(), tr_h, p,
+                                X_p.numpy(), Y_p.numpy(), q_p.numpy(), None, None)
+        else:
+            ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_HOST, nb, TX, RX, m, rows_h, row_scale, B_p.numpy(), tr_h, p,
+                                         X_p.numpy(), Y_p.numpy(), q_p.numpy(), None, None)
 
     step_host()
     barrier()
@@ -351,7 +394,7 @@ def ours_arm(args, wl, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = {"value": nb * world / float(e2e_s.item()), "unit": "solves/s",
-           "h2d_bytes_per_step": int(A_p.numel() * 8 + B_p.numel() * 8 + tr_h.nbytes),
+           "h2d_bytes_per_step": int((A_p.numel() * 8 if dense else rows_h.nbytes) + B_p.numel() * 8 + tr_h.nbytes),
            "d2h_bytes_per_step": int(X_p.numel() * 8 + Y_p.numel() * 8 + q_p.numel() * 8)}
     e2e_match = float(np.max(np.abs(X_p.numpy() - X_d.cpu().numpy())))   # same kernels, same inputs
 
@@ -359,7 +402,7 @@ def ours_arm(args, wl, rank, local_rank, world):
     cpu_baseline, nmse_delta = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sel = sample_instances(insts, cells, n_cells, per_cell=max(1, min(tpc, math.ceil(cores / n_cells))))
+        sel = sample_instances(insts, cells, n_cells, per_cell=max(1, min(tpc, math.ceil(2 * cores / n_cells))))
         sub = [insts[i] for i in sel]
         Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)), (TX, RX))
         cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": min(cores, len(sub)),
@@ -377,7 +420,10 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step_per_gpu": nb,
                            "trials_per_cell_per_gpu": tpc, "cells": n_cells,
-                           "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step)",
+                           "input_mode": "dense complex128 A per instance" if dense else
+                                         "codebook rows (codebook registered once; per step: row ids, RSS amplitudes, train splits)",
+                           "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step)" if dense else
+                                    "L2 flushed between steps (256 MB device memset on the solver's stream)",
                            "mean_iters_per_solve": float(info[:, 15].mean()),
                            "dedup_nuclear_rerun": bool(args.dedup_nuclear_rerun)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
@@ -591,13 +637,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-cs", type=int, default=None, help="cluster size of the r=20 stages (2 or 4)")
     ap.add_argument("--no-fast", action="store_true", help="force the general kernel")
+    ap.add_argument("--dense", action="store_true", help="ship a dense complex128 A per instance instead of codebook rows")
     ap.add_argument("--dedup-nuclear-rerun", action="store_true",
                     help="opt-in exact elision of the bit-identical rank-one rerun of inferLowRank_Nuclear "
                          "(not the default measurement: the literal reference flow is)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.trials_per_cell is None:
-        args.trials_per_cell = {"config1": 32, "config0": 512, "config3": 296, "config5": 148}[args.workload]
+        args.trials_per_cell = {"config1": 32, "config0": 512, "config3": 296, "config4": 37, "config5": 148}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

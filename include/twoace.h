@@ -189,6 +189,37 @@ int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_
 int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
                          const double* X_true, int phase_bit, double* out);
 
+/* ---- On-device instance synthesis -----------------------------------------------------
+ * Builds nb independent (trial, M, SNR) instances of the numerical-simulation workload on the GPU, so that the
+ * 100k / 1M-trial configurations need no per-instance host->device input traffic:
+ *   channel      Eq. 23 sparse multipath, L paths, AoD/AoA ~ U(-area/2, area/2) degrees, gains CN(0,1) normalised
+ *                (Numerical_Simulation/src/generate_channel/Generate_Channel.m:76-139)
+ *   probes       m_b rows without replacement from rows [row_lo_b, row_hi_b) of the registered codebook
+ *                (randperm, main/channel_recovery_ADMM_v2_simulation_A2only.m:137; ..._multiresolution.m:137-143)
+ *   RSS          B = | row_scale * cb[rows, :] vecH + CN(0, 10^(-snr_db/10)) |
+ *                (Numerical_Simulation/src/generate_measurement/Generate_Measurement.m:84-101)
+ *   train draws  ntrain draws of floor(m_b * cc_frac) measurement ids (randsample, inferLowRankV4.m:36-37)
+ * The random stream is Philox4x32-10 keyed by `seed` and counted by (index, stream, trial_id) -- see csrc/synth.cuh for
+ * the exact stream layout (restated by oracle/synth.py) -- so an instance depends only on (seed, trial_id): results
+ * are independent of batch composition and of how trials are sharded over GPUs.
+ * Index outputs (cb_rows: concat of m_b; train_idx: concat of ntrain x floor(m_b * cc_frac)) are written to HOST
+ * memory, ready to be passed to twoace_solve_batch_codebook; B (concat of m_b), vecH (nb x n complex) and angles
+ * (nb x 2L: AoD then AoA, degrees; may be NULL) follow `mem`.  row_hi_b - row_lo_b <= 8192. */
+typedef struct {
+  int32_t nt, nr, L;         /* transmit / receive antennas (n = nt * nr), paths (<= 32) */
+  double searching_area;     /* degrees: 95 (A2only.m:52) */
+  double wavelength;         /* 3e8 / 60.48e9 (A2only.m:38) */
+  double spacing;            /* 3.055e-3 (A2only.m:39) */
+  double row_scale;          /* 1 / sqrt(n): unit-norm probes, signal power 1 */
+  double cc_frac;            /* 0.95 */
+  int32_t ntrain;            /* 1, or 3 for inferLowRankV4_multi */
+  uint64_t seed;
+} twoace_synth_params;
+void twoace_synth_default_params(twoace_synth_params* p, int nt, int nr);
+int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_params* sp, const int32_t* m,
+                       const double* snr_db, const int32_t* row_lo, const int32_t* row_hi, const int64_t* trial_id,
+                       int32_t* cb_rows, int32_t* train_idx, double* B, double* vecH, double* angles);
+
 /* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
  * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
  * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass;

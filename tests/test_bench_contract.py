@@ -23,7 +23,7 @@ def test_contract_flops_per_iteration():
     assert abs(b.stage_flops(256, 64, 1, 16, False) - 0.49e6) < 0.01e6
     # the explicit-inverse branch wins once m is large (min of the two formulations)
     assert b.stage_flops(256, 1024, 20, 16, False) == 8 * 256 * 256 * 20 + 24 * 256 * 1024 * 20 + 16 * 16 * 256 * 20
-    assert set(b.WORKLOADS) == {"config0", "config1", "config3", "config5"}
+    assert set(b.WORKLOADS) == {"config0", "config1", "config3", "config4", "config5"}
 
 
 def test_reference_arm_prints_the_contract_line():

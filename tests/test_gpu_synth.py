@@ -1,0 +1,73 @@
+"""On-device instance synthesis (twoace_synth_batch, csrc/synth.cuh) against oracle/synth.py: integer outputs (probe
+rows, train draws) bit-exact, floating-point outputs (vecH, B, angles) to 1e-12 relative (libm vs CUDA sin/cos/log
+differ in the last ulp); and the synthesised instances solved end to end."""
+import numpy as np
+import pytest
+
+from oracle import admm, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cbname,ranges", [("random_probe_cb_16x16", [(0, 3968)]),
+                                           ("random_probe_cb_16x16_multires", [(0, 1984), (1984, 5952), (5952, 9920)])])
+def test_synth_matches_oracle(gpu_ctx, cbname, ranges):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    cb = hz.load_codebook(cbname)
+    gpu_ctx.set_codebook(cb)
+    Ms = [4, 36, 64, 121, 361, 1024]
+    m, lo, hi, snr, tid = [], [], [], [], []
+    for k, M in enumerate(Ms):
+        for j, (a, b) in enumerate(ranges):
+            m.append(M); lo.append(a); hi.append(b); snr.append(10.0 * (k % 4)); tid.append(1000 * k + j + (1 << 33) * (k == 2))
+    sp = tw.SynthParams.default(ntrain=3, seed=(7 << 32) + 58659179)
+    out = sv.synth_batch(m, snr, lo, hi, tid, sp, gpu_ctx)
+    for b in range(len(m)):
+        o = synth.synth_instance(cb, m[b], snr[b], lo[b], hi[b], tid[b], ntrain=3, seed=sp.seed)
+        assert np.array_equal(out["rows"][b], o["rows"])                       # bit-exact index bookkeeping
+        assert np.array_equal(out["train_idx"][b], o["train_idx"])
+        assert np.allclose(out["vecH"][b], o["vecH"], rtol=0, atol=1e-12 * np.abs(o["vecH"]).max())
+        assert np.allclose(out["B"][b], o["B"], rtol=0, atol=1e-12 * np.abs(o["B"]).max())
+        assert np.allclose(out["angles"][b], np.concatenate([o["aod"], o["aoa"]]), rtol=0, atol=1e-12)
+
+
+def test_synth_is_independent_of_batch_composition(gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    gpu_ctx.set_codebook(hz.load_codebook())
+    sp = tw.SynthParams.default()
+    a = sv.synth_batch([64, 32, 128], 20.0, 0, 3968, [5, 6, 7], sp, gpu_ctx)
+    b = sv.synth_batch([128], 20.0, 0, 3968, [7], sp, gpu_ctx)
+    assert np.array_equal(a["rows"][2], b["rows"][0]) and np.array_equal(a["B"][2], b["B"][0])
+    assert np.array_equal(a["vecH"][2], b["vecH"][0]) and np.array_equal(a["train_idx"][2], b["train_idx"][0])
+
+
+def test_synth_then_solve_matches_oracle_solve(gpu_ctx):
+    """Device-built instances through the codebook-mode solver == the oracle solver on the oracle-built instances."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    cb = hz.load_codebook()
+    gpu_ctx.set_codebook(cb)
+    sp = tw.SynthParams.default()
+    tid = list(range(40, 46))
+    out = sv.synth_batch([64] * 6, 20.0, 0, 3968, tid, sp, gpu_ctx)
+    res = sv.solve_batch_codebook(tw.V4, out["rows"], 1.0 / 16.0, out["B"], 16, 16, out["train_idx"], tw.Params.default(),
+                                  gpu_ctx)
+    errs = []
+    for b, t in enumerate(tid):
+        o = synth.synth_instance(cb, 64, 20.0, 0, 3968, t)
+        Xo, _, qo = admm.infer_low_rank_v4(cb[o["rows"]] / 16.0, o["B"], 16, 16, admm.Params(), train_idx=o["train_idx"][0])
+        errs.append(hz.aligned_rel_err(res.X[b], Xo))
+    errs = np.array(errs)
+    assert np.mean(errs <= 1e-4) >= 0.8, errs       # M = 64 default tolerances: the reference-determined regime
+
+
+def test_synth_errors(gpu_ctx):
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    gpu_ctx.set_codebook(hz.load_codebook())
+    with pytest.raises(tw.TwoaceError):
+        sv.synth_batch([64], 20.0, 0, 5000, [0], None, gpu_ctx)          # range beyond the codebook
+    with pytest.raises(tw.TwoaceError):
+        sv.synth_batch([300], 20.0, 0, 256, [0], None, gpu_ctx)          # more probes than candidate rows

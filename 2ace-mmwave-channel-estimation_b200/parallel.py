@@ -44,6 +44,21 @@ def local_stats(cell_ids, n_cells: int, mse, info, metrics=None) -> np.ndarray:
     return s
 
 
+def local_stats_device(cell_ids, n_cells: int, info, metrics):
+    """local_stats on the device with torch ops (no host round trip): cell_ids int64 [nb], info [nb,16],
+    metrics [nb,4] CUDA tensors -> [n_cells, len(METRICS)] float64 on the same device and stream."""
+    import torch
+    mse = metrics[:, 0]
+    ok = torch.isfinite(mse)
+    okf = ok.to(torch.float64)
+    z = torch.zeros_like(mse)
+    cols = [okf, torch.where(ok, mse, z), info[:, 2], info[:, 3], torch.nan_to_num(info[:, 0]), info[:, 15]]
+    cols += [torch.where(ok, torch.nan_to_num(metrics[:, 1 + k]), z) for k in range(3)]
+    payload = torch.stack(cols, dim=1)
+    s = torch.zeros((n_cells, len(METRICS)), dtype=torch.float64, device=mse.device)
+    return s.index_add_(0, cell_ids, payload)
+
+
 def all_reduce_stats(stats: np.ndarray, device=None) -> np.ndarray:
     """Sum the statistics tensor over all ranks (no-op without an initialised process group)."""
     import torch

@@ -89,13 +89,13 @@ def stage_flops(n, m, r, tx, nuclear):
     return core + (16 * n * r * r if nuclear else 16 * tx * n * r)
 
 
-def solve_flops(insts, stage_words, variant, cc_frac=0.95, rmax=20, N=N, TX=TX):
-    """Sum over instances and stages of iterations actually executed x per-iteration flops."""
+def solve_flops(ms, stage_words, variant, cc_frac=0.95, rmax=20, N=N, TX=TX):
+    """Sum over instances (ms: rows per instance) and stages of iterations actually executed x per-iteration flops."""
     T = 3 if variant == "V4_MULTI" else 1
     nuc = variant == "NUCLEAR"
     tot = 0.0
-    for b, ins in enumerate(insts):
-        m = len(ins.B)
+    for b, m in enumerate(ms):
+        m = int(m)
         mtr = int(math.floor(m * cc_frac))
         r = min(rmax, m, N)
         sw = stage_words[b]
@@ -147,7 +147,7 @@ def _noop(_):
     return 0
 
 
-def sample_instances(insts, cells, n_cells, per_cell=1):
+def sample_cells(cells, n_cells, per_cell=1):
     idx = []
     for c in range(n_cells):
         idx += list(np.nonzero(cells == c)[0][:per_cell])
@@ -247,6 +247,25 @@ def reference_arm(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def build_cells(wl, tpc, first_trial):
+    """Per-instance parameter lists of the synthesis (no data): tpc trials for every (M, SNR) cell.  The global trial
+    id (cell << 32 | trial) keys the Philox stream, so the set is independent of the rank count."""
+    from twoace_b200.entrypoints import multires_row_range
+    from twoace_b200 import harness as hz
+    cb = hz.load_codebook(wl.get("codebook", "random_probe_cb_16x16"))
+    m, snr, lo, hi, tid, cells = [], [], [], [], [], []
+    ci = 0
+    for M in wl["Ms"]:
+        for s in wl["snrs"]:
+            a, b = multires_row_range(M) if wl.get("multires") else (0, cb.shape[0])
+            for t in range(tpc):
+                m.append(M); snr.append(s); lo.append(a); hi.append(b); tid.append((ci << 32) | (first_trial + t))
+                cells.append(ci)
+            ci += 1
+    return (cb, np.array(m, np.int32), np.array(snr, np.float64), np.array(lo, np.int32), np.array(hi, np.int32),
+            np.array(tid, np.int64), np.array(cells), ci)
+
+
 def ours_arm(args, wl, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -269,47 +288,79 @@ def ours_arm(args, wl, rank, local_rank, world):
     TX, RX = wl.get("tx", 16), wl.get("rx", 16)
     N = TX * RX
     tpc = args.trials_per_cell
-    insts, cells, n_cells = build_instances(wl, tpc, rank * tpc)   # weak scaling: tpc trials per cell per GPU
-    nb = len(insts)
     p = tw.Params.default().fixed_iters()
-
-    m = np.array([len(i.B) for i in insts], dtype=np.int32)
-    dense = bool(args.dense) or N != 256
-    B_h = np.concatenate([i.B for i in insts])
-    tr_h = np.ascontiguousarray(np.concatenate([i.train_idx[:T].reshape(-1) for i in insts]).astype(np.int32))
-    sum_m = int(m.sum())
     nstage = 4 * T + 1
     row_scale = 1.0 / math.sqrt(N)
+    dense = bool(args.dense) or N != 256
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    W = tw.lib.METRIC_WORDS
+
     if dense:
+        # round-1 mode: instances built on the host (NumPy), a dense complex128 A per instance
+        insts, cells, n_cells = build_instances(wl, tpc, rank * tpc)
+        nb = len(insts)
+        m = np.array([len(i.B) for i in insts], dtype=np.int32)
+        B_h = np.concatenate([i.B for i in insts])
+        tr_h = np.ascontiguousarray(np.concatenate([i.train_idx[:T].reshape(-1) for i in insts]).astype(np.int32))
         A_h = np.concatenate([i.A.reshape(-1, order="F") for i in insts])
         A_d = torch.from_numpy(A_h.view(np.float64)).to(dev)
+        B_d = torch.from_numpy(B_h).to(dev)
+        Xt_d = torch.from_numpy(np.ascontiguousarray(np.stack([i.vecH for i in insts])).view(np.float64)).to(dev)
         rows_h = None
-    else:   # codebook mode: the codebook is registered once (like the .mat file the entry points load)
-        ctx.set_codebook(wl["_cb"])
-        rows_h = np.ascontiguousarray(np.concatenate([i.rows for i in insts]).astype(np.int32))
+        sp = None
+    else:
+        # instances built on the device from the registered codebook (twoace_synth_batch); the codebook is uploaded
+        # once, like the .mat file the reference's entry points load (A2only.m:120)
+        cb, m, snr, lo, hi, tid, cells, n_cells = build_cells(wl, tpc, rank * tpc)
+        nb = len(m)
+        ctx.set_codebook(cb)
+        sp = tw.SynthParams.default(TX, RX, ntrain=T, seed=hz.BASE_SEED)
+        mtr = np.floor(m * sp.cc_frac).astype(np.int64)
+        rows_h = np.empty(int(m.sum()), np.int32)
+        tr_h = np.empty(int((mtr * T).sum()), np.int32)
+        B_d = torch.empty(int(m.sum()), dtype=torch.float64, device=dev)
+        Xt_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
+        ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows_h, tr_h, B_d.data_ptr(), Xt_d.data_ptr())
+        B_h = B_d.cpu().numpy()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # L2 flush between steps (126 MB L2)
+    sum_m = int(m.sum())
+    cells_d = torch.from_numpy(np.asarray(cells, dtype=np.int64)).to(dev)
 
     # ---- device-resident inputs/outputs (the `value` leg)
-    B_d = torch.from_numpy(B_h).to(dev)
     X_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
     Y_d = torch.empty(sum_m * 2, dtype=torch.float64, device=dev)
     q_d = torch.empty(nb, dtype=torch.float64, device=dev)
     info_d = torch.empty(nb * 16, dtype=torch.float64, device=dev)
     sw_d = torch.empty(nb * nstage * tw.lib.STAGE_WORDS, dtype=torch.float64, device=dev)
+    met_d = torch.empty(nb * W, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    stats_box = [None]
 
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-
-    def step_device():
+    def solve_device():
         if dense:
             ctx.solve_batch_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, A_d.data_ptr(), B_d.data_ptr(), tr_h, p,
                                 X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), sw_d.data_ptr())
         else:
-            with torch.cuda.stream(stream):
-                flush.zero_()
             ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, rows_h, row_scale, B_d.data_ptr(),
                                          tr_h, p, X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(),
                                          sw_d.data_ptr())
+
+    def evaluate_and_reduce():
+        """Evaluation metrics on the device (Evaluation_H.m:81-115), per-cell sums, and the ONE collective of the path:
+        the all-reduce of the statistics tensor (NCCL over NVLink when world > 1) -- all inside the timed step."""
+        ctx.metrics_batch_raw(tw.lib.MEM_DEVICE, nb, TX, RX, X_d.data_ptr(), Xt_d.data_ptr(), 2, met_d.data_ptr())
+        with torch.cuda.stream(stream):
+            st = par.local_stats_device(cells_d, n_cells, info_d.view(nb, 16), met_d.view(nb, W))
+            if world > 1:
+                dist.all_reduce(st)
+        stats_box[0] = st
+
+    def step_device():
+        if not dense:
+            with torch.cuda.stream(stream):
+                flush.zero_()
+        solve_device()
+        evaluate_and_reduce()
 
     def barrier():
         if world > 1:
@@ -342,31 +393,27 @@ def ours_arm(args, wl, rank, local_rank, world):
     ms_step = float(t.item()) / args.steps
     value = nb * world / (ms_step * 1e-3)
 
-    # ---- statistics reduce (the one collective of the path), outside the timed region
     X = X_d.cpu().numpy().view(np.complex128).reshape(nb, N)
     info = info_d.cpu().numpy().reshape(nb, 16)
     sw = sw_d.cpu().numpy().reshape(nb, nstage, tw.lib.STAGE_WORDS)
-    # evaluation metrics on the device (Evaluation_H.m:81-115): the payload of the reduce
-    Xt_d = torch.from_numpy(np.ascontiguousarray(np.stack([i.vecH for i in insts])).view(np.float64)).to(dev)
-    met_d = torch.empty(nb * tw.lib.METRIC_WORDS, dtype=torch.float64, device=dev)
-    ctx.metrics_batch_raw(tw.lib.MEM_DEVICE, nb, TX, RX, X_d.data_ptr(), Xt_d.data_ptr(), 2, met_d.data_ptr())
-    ctx.synchronize()
-    met = met_d.cpu().numpy().reshape(nb, tw.lib.METRIC_WORDS)
-    mse = met[:, 0]
-    stats = par.all_reduce_stats(par.local_stats(cells, n_cells, mse, info, met), dev if world > 1 else None)
+    stats = stats_box[0].cpu().numpy()
 
-    # ---- roofline of the dominant kernel (admm_stage_kernel), live CUDA-event durations
-    flops_step = solve_flops(insts, sw, wl["variant"], N=N, TX=TX)
+    # ---- roofline of the dominant kernels (the InferADMM stage kernels), live CUDA-event durations
+    flops_step = solve_flops(m, sw, wl["variant"], N=N, TX=TX)
     peak = ctx.fp64_peak_tflops()
     achieved = flops_step * args.steps / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                "kernel": "InferADMM stage kernels (fast_stage_kernel<RL,CS> where eligible, else admm_stage_kernel)",
+                "kernel": "InferADMM stage kernels (fast_stage_kernel<RL,CS> / big_stage_kernel / big1_stage_kernel where "
+                          "eligible, else admm_stage_kernel)",
                 "fast_kernel_launches": int(ctx.fast_launch_count), "kernel_ms_per_step": stage_ms / args.steps,
                 "kernel_launches_per_step": stage_launches / args.steps,
                 "kernel_share_of_step": stage_ms / ms_total,
                 "peak_source": "measured live: twoace_fp64_peak DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 figure)",
-                "flops_per_step": flops_step}
+                "flops_per_step": flops_step,
+                "note": "contract flops (SURVEY 8d: three A-products + A'Y + full ArgMinZ every iteration) over the "
+                        "stage-kernel time; the kernels execute two A-products and screen most eigensolves, so the "
+                        "FP64-pipe utilisation ncu reports is lower (profiles/)"}
 
     # ---- end to end through the public C ABI with pinned HOST buffers (H2D + D2H inside the region)
     A_p = torch.from_numpy(A_h.view(np.float64)).pin_memory() if dense else None
@@ -384,32 +431,66 @@ def ours_arm(args, wl, rank, local_rank, world):
             ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_HOST, nb, TX, RX, m, rows_h, row_scale, B_p.numpy(), tr_h, p,
                                          X_p.numpy(), Y_p.numpy(), q_p.numpy(), None, None)
 
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()          # synchronous: returns after the D2H copies have landed
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e = {"value": nb * world / float(e2e_s.item()), "unit": "solves/s",
-           "h2d_bytes_per_step": int((A_p.numel() * 8 if dense else rows_h.nbytes) + B_p.numel() * 8 + tr_h.nbytes),
+    def timed_host(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()             # synchronous: returns after the D2H copies have landed
+        barrier()
+        ts = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        return nb * world / float(ts.item())
+
+    e2e = {"value": timed_host(step_host), "unit": "solves/s",
+           "h2d_bytes_per_step": int((A_p.numel() * 8 if dense else rows_h.nbytes) + B_p.numel() * 8 + tr_h.nbytes + m.nbytes),
            "d2h_bytes_per_step": int(X_p.numel() * 8 + Y_p.numel() * 8 + q_p.numel() * 8)}
     e2e_match = float(np.max(np.abs(X_p.numpy() - X_d.cpu().numpy())))   # same kernels, same inputs
 
+    # ---- the whole simulation step on the device: synthesis -> solve -> metrics -> statistics, results to the host
+    e2e_synth = None
+    if not dense:
+        met_p = torch.empty(nb * W, dtype=torch.float64).pin_memory()
+        rows2, tr2 = np.empty_like(rows_h), np.empty_like(tr_h)
+
+        def step_synth():
+            ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows2, tr2, B_d.data_ptr(), Xt_d.data_ptr())
+            ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, rows2, row_scale, B_d.data_ptr(), tr2, p,
+                                         X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), None)
+            evaluate_and_reduce()
+            with torch.cuda.stream(stream):
+                X_p.copy_(X_d, non_blocking=True)
+                met_p.copy_(met_d, non_blocking=True)
+            ctx.synchronize()
+
+        e2e_synth = {"value": timed_host(step_synth), "unit": "solves/s",
+                     "h2d_bytes_per_step": int(m.nbytes + snr.nbytes + lo.nbytes + hi.nbytes + tid.nbytes + rows2.nbytes + tr2.nbytes),
+                     "d2h_bytes_per_step": int(rows2.nbytes + tr2.nbytes + X_p.numel() * 8 + met_p.numel() * 8),
+                     "what": "twoace_synth_batch + twoace_solve_batch_codebook + twoace_metrics_batch + statistics "
+                             "reduce per step, instances never leave the device"}
+
     # ---- CPU baseline + NMSE delta on a bounded sample (rank 0, N=1 only)
     cpu_baseline, nmse_delta = None, None
+    Xt = Xt_d.cpu().numpy().view(np.complex128).reshape(nb, N)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sel = sample_instances(insts, cells, n_cells, per_cell=max(1, min(tpc, math.ceil(2 * cores / n_cells))))
-        sub = [insts[i] for i in sel]
+        sel = sample_cells(cells, n_cells, per_cell=max(1, min(tpc, math.ceil(2 * cores / n_cells))))
+        if dense:
+            sub = [insts[i] for i in sel]
+        else:   # the same instances restated by the oracle's generator (equal to 1e-12; tests/test_gpu_synth.py)
+            from oracle import synth as osyn
+            sub = []
+            for i in sel:
+                o = osyn.synth_instance(cb, int(m[i]), float(snr[i]), int(lo[i]), int(hi[i]), int(tid[i]), nt=TX, nr=RX,
+                                        ntrain=T, seed=hz.BASE_SEED)
+                sub.append(hz.Instance(o["rows"], cb[o["rows"]] * row_scale, o["B"], o["train_idx"], o["vecH"], float(snr[i])))
         Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)), (TX, RX))
         cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": min(cores, len(sub)),
                         "kind": "port",
                         "sample": f"{len(sub)} of the step's {nb} instances ({len(sub) // n_cells} per (M,SNR) cell), "
-                                  f"NumPy oracle, 1 BLAS thread per process, {wall:.1f} s wall"}
-        g = hz.nmse_db([hz.nmse(X[i], insts[i].vecH) for i in sel])
+                                  f"NumPy oracle, 1 BLAS thread per process, longest job first, {wall:.1f} s wall"}
+        g = hz.nmse_db([hz.nmse(X[i], Xt[i]) for i in sel])
         o = hz.nmse_db([hz.nmse(Xo[k], sub[k].vecH) for k in range(len(sub))])
         nmse_delta = g - o
 
@@ -420,13 +501,16 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step_per_gpu": nb,
                            "trials_per_cell_per_gpu": tpc, "cells": n_cells,
-                           "input_mode": "dense complex128 A per instance" if dense else
-                                         "codebook rows (codebook registered once; per step: row ids, RSS amplitudes, train splits)",
+                           "input_mode": "dense complex128 A per instance, instances built on the host" if dense else
+                                         "codebook rows (codebook registered once); instances built on the device by "
+                                         "twoace_synth_batch (Philox4x32-10 keyed by the global trial id)",
+                           "timed_step": "solve + evaluation metrics + per-cell statistics + all-reduce of the statistics",
                            "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step)" if dense else
                                     "L2 flushed between steps (256 MB device memset on the solver's stream)",
                            "mean_iters_per_solve": float(info[:, 15].mean()),
                            "dedup_nuclear_rerun": bool(args.dedup_nuclear_rerun)},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_synth": e2e_synth,
+                "gpu_launches": int(launches),
                 "clocks": clocks, "nmse_delta_db": nmse_delta,
                 "nmse_db_per_cell": [None if not np.isfinite(v) else float(v) for v in par.nmse_db_per_cell(stats)],
                 "metrics_mean": {k: float(stats[:, 6 + j].sum() / max(stats[:, 0].sum(), 1.0))

@@ -14,6 +14,7 @@
 #include "phaselift.cuh"
 #include "metrics.cuh"
 #include "synth.cuh"
+#include <thread>
 
 using namespace twoace;
 
@@ -46,6 +47,7 @@ struct twoace_ctx {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
   std::vector<std::string> stage_labels;   // one per stage_events entry (TWOACE_TRACE_LAUNCHES=1 prints them)
+  std::vector<twoace_ctx*> peers;          // twoace_create_multi: the contexts of the other GPUs (this one is device 0 of the set)
 };
 
 #define CK(call)                                                                              \
@@ -126,6 +128,8 @@ extern "C" int twoace_create(int device, twoace_ctx** out) {
 
 extern "C" void twoace_destroy(twoace_ctx* ctx) {
   if (!ctx) return;
+  for (twoace_ctx* p : ctx->peers) twoace_destroy(p);
+  ctx->peers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.p) cudaFree(ctx->arena.p);
@@ -139,12 +143,85 @@ extern "C" void twoace_destroy(twoace_ctx* ctx) {
 
 extern "C" const char* twoace_last_error(const twoace_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* twoace_stream(twoace_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-extern "C" int64_t twoace_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t twoace_launch_count(const twoace_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t n = ctx->launches;
+  for (const twoace_ctx* p : ctx->peers) n += p->launches;
+  return n;
+}
 extern "C" int twoace_synchronize(twoace_ctx* ctx) {
   if (!ctx) return TWOACE_E_INVALID;
+  for (twoace_ctx* p : ctx->peers) { int rc = twoace_synchronize(p); if (rc) { ctx->err = p->err; return rc; } }
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return TWOACE_OK;
+}
+
+// ---- several GPUs behind one context (instances are independent, each GPU owns a contiguous slice)
+extern "C" int twoace_create_multi(const int* devices, int n_dev, twoace_ctx** out) {
+  if (!out) return TWOACE_E_INVALID;
+  *out = nullptr;
+  if (!devices || n_dev < 1) return TWOACE_E_INVALID;
+  for (int i = 0; i < n_dev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return TWOACE_E_INVALID;
+  twoace_ctx* c = nullptr;
+  int rc = twoace_create(devices[0], &c);
+  if (rc) return rc;
+  for (int i = 1; i < n_dev; ++i) {
+    twoace_ctx* p = nullptr;
+    rc = twoace_create(devices[i], &p);
+    if (rc) { twoace_destroy(c); return rc; }
+    c->peers.push_back(p);
+  }
+  *out = c;
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_device_count(const twoace_ctx* ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
+
+// Contiguous slices of a ragged batch, balanced by the row counts (the cost of a solve grows with m).
+struct BatchSlice { int b0, b1; size_t rows0; };   // instances [b0, b1), rows0 = sum of m over [0, b0)
+static std::vector<BatchSlice> split_batch(const int32_t* m, int nb, int parts) {
+  std::vector<size_t> pre(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) pre[b + 1] = pre[b] + (m ? (size_t)std::max(1, m[b]) : 1);
+  std::vector<BatchSlice> out;
+  int b0 = 0;
+  for (int k = 0; k < parts; ++k) {
+    int b1 = nb;
+    if (k + 1 < parts) {
+      const size_t want = pre[nb] * (size_t)(k + 1) / parts;
+      b1 = (int)(std::lower_bound(pre.begin(), pre.end(), want) - pre.begin());
+      b1 = std::min(std::max(b1, b0), nb);
+    }
+    size_t rows0 = 0;
+    if (m) for (int b = 0; b < b0; ++b) rows0 += m[b];
+    out.push_back({b0, b1, rows0});
+    b0 = b1;
+  }
+  return out;
+}
+
+// Run f(context of GPU k, slice k) on one host thread per GPU; the first failure is reported through `ctx`.
+template <class F>
+static int run_on_all(twoace_ctx* ctx, const std::vector<BatchSlice>& sl, F f) {
+  const int parts = (int)sl.size();
+  std::vector<int> rcs(parts, 0);
+  std::vector<std::thread> th;
+  auto sub = [&](int k) { return k == 0 ? ctx : ctx->peers[k - 1]; };
+  for (int k = 1; k < parts; ++k)
+    th.emplace_back([&, k]() { rcs[k] = sl[k].b1 > sl[k].b0 ? f(sub(k), sl[k]) : 0; });
+  rcs[0] = sl[0].b1 > sl[0].b0 ? f(ctx, sl[0]) : 0;
+  for (auto& t : th) t.join();
+  for (int k = 1; k < parts; ++k)
+    if (rcs[k]) { ctx->err = "GPU " + std::to_string(sub(k)->device) + ": " + sub(k)->err; return rcs[k]; }
+  return rcs[0];
+}
+
+static int multi_guard(twoace_ctx* ctx, int mem) {
+  if (mem != TWOACE_MEM_HOST) FAIL(TWOACE_E_INVALID, "a multi-GPU context takes host buffers only (mem = TWOACE_MEM_HOST)");
+  if (ctx->trace_user) FAIL(TWOACE_E_UNSUPPORTED, "the residual trace is not available on a multi-GPU context");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -944,6 +1021,35 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
   return TWOACE_OK;
 }
 
+// One GPU: solve_common.  Several (twoace_create_multi): every GPU solves a contiguous slice of the batch on its own
+// host thread; the outputs land in the caller's (host) buffers at the slice offsets.
+static int solve_multi(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx, const int32_t* m,
+                       const double* A, const int32_t* cb_rows, double row_scale, const double* B,
+                       const int32_t* train_idx, const twoace_params* params, double* X, double* Y,
+                       double* quality, double* info, double* stage_words) {
+  if (!ctx || ctx->peers.empty() || nb < 2 || !m)
+    return solve_common(ctx, variant, mem, nb, tx, rx, m, A, cb_rows, row_scale, B, train_idx, params, X, Y, quality, info, stage_words);
+  ctx->err.clear();
+  int rc = multi_guard(ctx, mem);
+  if (rc) return rc;
+  if (!B || !train_idx || !X || !Y || !quality) FAIL(TWOACE_E_INVALID, "null argument");
+  twoace_params p;
+  if (params) p = *params; else twoace_default_params(&p);
+  const int T = variant == TWOACE_V4_MULTI ? 3 : 1, nstage = 4 * T + 1;
+  const size_t n = (size_t)tx * rx;
+  for (int b = 0; b < nb; ++b) if (m[b] < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m[b]);
+  std::vector<size_t> tr_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) tr_off[b + 1] = tr_off[b] + (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+  const auto sl = split_batch(m, nb, 1 + (int)ctx->peers.size());
+  return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
+    return solve_common(c, variant, mem, s.b1 - s.b0, tx, rx, m + s.b0, A ? A + 2 * s.rows0 * n : nullptr,
+                        cb_rows ? cb_rows + s.rows0 : nullptr, row_scale, B + s.rows0, train_idx + tr_off[s.b0], &p,
+                        X + 2 * (size_t)s.b0 * n, Y + 2 * s.rows0, quality + s.b0,
+                        info ? info + (size_t)s.b0 * TWOACE_INFO_WORDS : nullptr,
+                        stage_words ? stage_words + (size_t)s.b0 * nstage * STAGE_SCAL : nullptr);
+  });
+}
+
 extern "C" int twoace_set_trace(twoace_ctx* ctx, int mem, double* trace, int64_t capacity) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
@@ -958,7 +1064,7 @@ extern "C" int twoace_solve_batch(twoace_ctx* ctx, int variant, int mem, int nb,
                                   const twoace_params* params, double* X, double* Y, double* quality,
                                   double* info, double* stage_words) {
   if (ctx && !A) { ctx->err = "A is null"; return TWOACE_E_INVALID; }
-  return solve_common(ctx, variant, mem, nb, tx, rx, m, A, nullptr, 1.0, B, train_idx, params, X, Y, quality, info, stage_words);
+  return solve_multi(ctx, variant, mem, nb, tx, rx, m, A, nullptr, 1.0, B, train_idx, params, X, Y, quality, info, stage_words);
 }
 
 extern "C" int twoace_solve_batch_codebook(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx,
@@ -966,7 +1072,7 @@ extern "C" int twoace_solve_batch_codebook(twoace_ctx* ctx, int variant, int mem
                                            const double* B, const int32_t* train_idx, const twoace_params* params,
                                            double* X, double* Y, double* quality, double* info, double* stage_words) {
   if (ctx && !cb_rows) { ctx->err = "cb_rows is null"; return TWOACE_E_INVALID; }
-  return solve_common(ctx, variant, mem, nb, tx, rx, m, nullptr, cb_rows, row_scale, B, train_idx, params, X, Y, quality, info, stage_words);
+  return solve_multi(ctx, variant, mem, nb, tx, rx, m, nullptr, cb_rows, row_scale, B, train_idx, params, X, Y, quality, info, stage_words);
 }
 
 __global__ void transpose_cm_to_rm(const cd* __restrict__ src, cd* __restrict__ dst, int rows, int n) {
@@ -982,6 +1088,13 @@ extern "C" int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, co
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
   if (rows < 1 || n < 1 || !cb) FAIL(TWOACE_E_INVALID, "bad codebook arguments");
+  if (!ctx->peers.empty()) {   // every GPU of a multi-GPU context holds its own copy
+    if (mem != TWOACE_MEM_HOST) FAIL(TWOACE_E_INVALID, "a multi-GPU context takes the codebook from host memory");
+    for (twoace_ctx* p : ctx->peers) {
+      const int rc = twoace_set_codebook(p, mem, rows, n, cb);
+      if (rc) { ctx->err = p->err; return rc; }
+    }
+  }
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->cb_rm) { CK(cudaFree(ctx->cb_rm)); ctx->cb_rm = nullptr; }
@@ -1206,7 +1319,7 @@ extern "C" void twoace_pl_default_opts(twoace_pl_opts* o) {
   o->L0 = 1.0; o->cntr_reset = 50; o->backtrack_tol = 1e-10; o->reduce = 1;
 }
 
-extern "C" int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
+static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
                                       const int32_t* cb_rows, double row_scale, const double* y,
                                       const twoace_pl_opts* opts, double* sig, double* info) {
   if (!ctx) return TWOACE_E_INVALID;
@@ -1309,8 +1422,8 @@ extern "C" int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, c
 
 // ------------------------------------------------------------------------------------------
 // Evaluation metrics (Evaluation_H.m:81-115)
-extern "C" int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
-                                    const double* X_true, int phase_bit, double* out) {
+static int metrics_single(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
+                          const double* X_true, int phase_bit, double* out) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
   if (nb < 0 || !X_est || !X_true || !out) FAIL(TWOACE_E_INVALID, "null argument");
@@ -1342,10 +1455,10 @@ extern "C" void twoace_synth_default_params(twoace_synth_params* p, int nt, int 
   p->row_scale = 1.0 / std::sqrt((double)nt * nr); p->cc_frac = 0.95; p->ntrain = 1; p->seed = 58659179ull;
 }
 
-extern "C" int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_params* sp, const int32_t* m,
-                                  const double* snr_db, const int32_t* row_lo, const int32_t* row_hi,
-                                  const int64_t* trial_id, int32_t* cb_rows, int32_t* train_idx, double* B,
-                                  double* vecH, double* angles) {
+static int synth_single(twoace_ctx* ctx, int mem, int nb, const twoace_synth_params* sp, const int32_t* m,
+                        const double* snr_db, const int32_t* row_lo, const int32_t* row_hi,
+                        const int64_t* trial_id, int32_t* cb_rows, int32_t* train_idx, double* B,
+                        double* vecH, double* angles) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
   if (nb < 0 || !sp || !m || !snr_db || !row_lo || !row_hi || !trial_id || !cb_rows || !train_idx || !B || !vecH)
@@ -1411,6 +1524,60 @@ extern "C" int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace
   rc = host_back(ctx, mem, angles, dAng, (size_t)nb * 2 * sp->L * sizeof(double)); if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));   // the index lists are host outputs
   return TWOACE_OK;
+}
+
+extern "C" int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
+                                      const int32_t* cb_rows, double row_scale, const double* y,
+                                      const twoace_pl_opts* opts, double* sig, double* info) {
+  if (!ctx || ctx->peers.empty() || nb < 2 || !m)
+    return phaselift_single(ctx, mem, nb, n, m, A, cb_rows, row_scale, y, opts, sig, info);
+  ctx->err.clear();
+  int rc = multi_guard(ctx, mem);
+  if (rc) return rc;
+  if (!y || !sig) FAIL(TWOACE_E_INVALID, "null argument");
+  const auto sl = split_batch(m, nb, 1 + (int)ctx->peers.size());
+  return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
+    return phaselift_single(c, mem, s.b1 - s.b0, n, m + s.b0, A ? A + 2 * s.rows0 * (size_t)n : nullptr,
+                            cb_rows ? cb_rows + s.rows0 : nullptr, row_scale, y + s.rows0, opts,
+                            sig + 2 * (size_t)s.b0 * n, info ? info + (size_t)s.b0 * TWOACE_PL_INFO_WORDS : nullptr);
+  });
+}
+
+extern "C" int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
+                                    const double* X_true, int phase_bit, double* out) {
+  if (!ctx || ctx->peers.empty() || nb < 2) return metrics_single(ctx, mem, nb, tx, rx, X_est, X_true, phase_bit, out);
+  ctx->err.clear();
+  int rc = multi_guard(ctx, mem);
+  if (rc) return rc;
+  if (!X_est || !X_true || !out) FAIL(TWOACE_E_INVALID, "null argument");
+  const size_t n = (size_t)tx * rx;
+  const auto sl = split_batch(nullptr, nb, 1 + (int)ctx->peers.size());
+  return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
+    return metrics_single(c, mem, s.b1 - s.b0, tx, rx, X_est + 2 * (size_t)s.b0 * n, X_true + 2 * (size_t)s.b0 * n, phase_bit,
+                          out + (size_t)s.b0 * MET_WORDS);
+  });
+}
+
+extern "C" int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_params* sp, const int32_t* m,
+                                  const double* snr_db, const int32_t* row_lo, const int32_t* row_hi,
+                                  const int64_t* trial_id, int32_t* cb_rows, int32_t* train_idx, double* B,
+                                  double* vecH, double* angles) {
+  if (!ctx || ctx->peers.empty() || nb < 2 || !m || !sp)
+    return synth_single(ctx, mem, nb, sp, m, snr_db, row_lo, row_hi, trial_id, cb_rows, train_idx, B, vecH, angles);
+  ctx->err.clear();
+  int rc = multi_guard(ctx, mem);
+  if (rc) return rc;
+  if (!snr_db || !row_lo || !row_hi || !trial_id || !cb_rows || !train_idx || !B || !vecH) FAIL(TWOACE_E_INVALID, "null argument");
+  if (sp->ntrain < 1 || !(sp->cc_frac > 0.0 && sp->cc_frac < 1.0)) FAIL(TWOACE_E_INVALID, "bad synthesis parameters");
+  std::vector<size_t> tr_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) tr_off[b + 1] = tr_off[b] + (size_t)sp->ntrain * (size_t)std::floor((double)std::max(0, m[b]) * sp->cc_frac);
+  const size_t n = (size_t)sp->nt * sp->nr;
+  const auto sl = split_batch(m, nb, 1 + (int)ctx->peers.size());
+  return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
+    return synth_single(c, mem, s.b1 - s.b0, sp, m + s.b0, snr_db + s.b0, row_lo + s.b0, row_hi + s.b0, trial_id + s.b0,
+                        cb_rows + s.rows0, train_idx + tr_off[s.b0], B + s.rows0, vecH + 2 * (size_t)s.b0 * n,
+                        angles ? angles + (size_t)s.b0 * 2 * sp->L : nullptr);
+  });
 }
 
 extern "C" int twoace_set_timing(twoace_ctx* ctx, int on) {
@@ -1486,6 +1653,7 @@ extern "C" int twoace_fp64_peak(twoace_ctx* ctx, double* tflops) {
 extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return TWOACE_E_INVALID;
   ctx->err.clear();
+  for (twoace_ctx* p : ctx->peers) { const int rc = twoace_set_option(p, key, value); if (rc) { ctx->err = p->err; return rc; } }
   const std::string k(key);
   if (k == "fast") ctx->opt_fast = value ? 1 : 0;
   else if (k == "fast_cs") { if (value != 2 && value != 4) FAIL(TWOACE_E_INVALID, "fast_cs must be 2 or 4"); ctx->opt_fast_cs = value; }
@@ -1497,5 +1665,15 @@ extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   return TWOACE_OK;
 }
 
-extern "C" int64_t twoace_fast_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->fast_launches : 0; }
-extern "C" int64_t twoace_tensor_launch_count(const twoace_ctx* ctx) { return ctx ? ctx->tc_launches : 0; }
+extern "C" int64_t twoace_fast_launch_count(const twoace_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t n = ctx->fast_launches;
+  for (const twoace_ctx* p : ctx->peers) n += p->fast_launches;
+  return n;
+}
+extern "C" int64_t twoace_tensor_launch_count(const twoace_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t n = ctx->tc_launches;
+  for (const twoace_ctx* p : ctx->peers) n += p->tc_launches;
+  return n;
+}

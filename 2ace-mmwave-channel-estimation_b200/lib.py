@@ -25,6 +25,7 @@ EXPORTS = [
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
     "twoace_set_option", "twoace_fast_launch_count", "twoace_tensor_launch_count", "twoace_set_trace", "twoace_pl_default_opts", "twoace_phaselift_batch",
     "twoace_metrics_batch", "twoace_synth_default_params", "twoace_synth_batch",
+    "twoace_create_multi", "twoace_device_count",
 ]
 
 
@@ -106,6 +107,10 @@ def load() -> C.CDLL:
     lib.twoace_version.restype = C.c_int
     lib.twoace_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.twoace_create.restype = C.c_int
+    lib.twoace_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.twoace_create_multi.restype = C.c_int
+    lib.twoace_device_count.argtypes = [vp]
+    lib.twoace_device_count.restype = C.c_int
     lib.twoace_destroy.argtypes = [vp]
     lib.twoace_destroy.restype = None
     lib.twoace_last_error.argtypes = [vp]
@@ -170,17 +175,26 @@ def _ptr(a):
 
 
 class Context:
-    """twoace_ctx wrapper (one per GPU / process)."""
+    """twoace_ctx wrapper: one GPU (``Context(0)``) or several GPUs of a node behind one context
+    (``Context([0, 1, 2, 3])``, twoace_create_multi: batches are split into per-GPU slices, host buffers only)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.lib = load()
         h = C.c_void_p()
-        rc = self.lib.twoace_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.twoace_create_multi(arr, len(device), C.byref(h))
+        else:
+            rc = self.lib.twoace_create(int(device), C.byref(h))
         if rc != 0 or not h.value:
             raise TwoaceError(f"twoace_create(device={device}) failed with code {rc}: no usable CUDA device "
                               "(the product path has no CPU fallback)")
         self.h = h
         self.device = device
+
+    @property
+    def device_count(self) -> int:
+        return int(self.lib.twoace_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

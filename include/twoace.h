@@ -81,6 +81,15 @@ void twoace_default_params(twoace_params* p);
 int twoace_version(void);
 
 int twoace_create(int device, twoace_ctx** ctx);
+/* One context over several GPUs of a node (twoace_create(device_ids, n_dev, &ctx)).  Instances
+ * are independent, so every batched entry point (solve_batch, solve_batch_codebook, phaselift_batch, metrics_batch,
+ * synth_batch) splits its batch into contiguous slices balanced by row count, one per GPU, each driven by its own
+ * host thread; results land in the caller's buffers at the slice offsets and do not depend on the GPU count.
+ * A multi-GPU context takes HOST buffers only; codebook and options are replicated on every GPU; the residual trace
+ * is not available.  The per-stage test entry points (infer_admm_batch, spectral_init_batch) run on the first GPU. */
+int twoace_create_multi(const int* devices, int n_dev, twoace_ctx** ctx);
+/* GPUs behind the context (1 for twoace_create). */
+int twoace_device_count(const twoace_ctx* ctx);
 void twoace_destroy(twoace_ctx* ctx);
 const char* twoace_last_error(const twoace_ctx* ctx);
 /* CUDA stream the context launches on (cudaStream_t as void*), for event timing by callers. */

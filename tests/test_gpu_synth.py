@@ -71,3 +71,35 @@ def test_synth_errors(gpu_ctx):
         sv.synth_batch([64], 20.0, 0, 5000, [0], None, gpu_ctx)          # range beyond the codebook
     with pytest.raises(tw.TwoaceError):
         sv.synth_batch([300], 20.0, 0, 256, [0], None, gpu_ctx)          # more probes than candidate rows
+
+
+def test_multi_gpu_context_equals_single_gpu(gpu_ctx):
+    """twoace_create_multi: the batch is split over the GPUs behind one context; results are identical to one GPU
+    (bitwise: the kernel an instance runs on never depends on its batch mates).  With one visible GPU the same
+    device cannot be listed twice, so the context degenerates to one slice and the test still exercises the path."""
+    import torch
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    ndev = torch.cuda.device_count()
+    mctx = tw.Context(list(range(ndev)))
+    assert mctx.device_count == ndev
+    cb = hz.load_codebook()
+    for c in (gpu_ctx, mctx):
+        c.set_codebook(cb)
+    sp = tw.SynthParams.default(ntrain=3)
+    Ms = [64, 36, 121, 64, 32, 225, 64]
+    a = sv.synth_batch(Ms, 20.0, 0, 3968, list(range(7)), sp, gpu_ctx)
+    b = sv.synth_batch(Ms, 20.0, 0, 3968, list(range(7)), sp, mctx)
+    for k in range(7):
+        assert np.array_equal(a["rows"][k], b["rows"][k]) and np.array_equal(a["B"][k], b["B"][k])
+        assert np.array_equal(a["train_idx"][k], b["train_idx"][k])
+    p = tw.Params.default(maxiter=60)
+    r1 = sv.solve_batch_codebook(tw.V4_MULTI, a["rows"], 1 / 16, a["B"], 16, 16, a["train_idx"], p, gpu_ctx)
+    r2 = sv.solve_batch_codebook(tw.V4_MULTI, a["rows"], 1 / 16, a["B"], 16, 16, a["train_idx"], p, mctx)
+    assert np.array_equal(r1.X, r2.X) and np.array_equal(r1.quality, r2.quality)
+    for k in range(7):
+        assert np.array_equal(r1.Y[k], r2.Y[k])
+    m1 = sv.evaluation_batch(r1.X, a["vecH"], 16, 16, ctx=gpu_ctx)
+    m2 = sv.evaluation_batch(r2.X, a["vecH"], 16, 16, ctx=mctx)
+    assert np.array_equal(np.asarray(m1), np.asarray(m2), equal_nan=True)
+    mctx.close()

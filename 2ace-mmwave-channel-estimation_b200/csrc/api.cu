@@ -39,6 +39,7 @@ struct twoace_ctx {
   int opt_fast_cs = 2;   // cluster size for the r = 20 stages (2 or 4)
   int opt_dedup_nuclear = 0;   // 1: do not re-execute the (bit-identical) rank-one rerun of inferLowRank_Nuclear
   int opt_cache_sinv = 1;   // 1: the stages of a trial share one (I + A A')^-1 (computed by the first of them)
+  int opt_spectral_jacobi = 0;   // 1: full Jacobi eigendecomposition in the spectral initialisation (round-1 path)
   int opt_tensor = 1;    // 1: exact int8 tensor-core (tcgen05) A-products in the cluster kernel, 0: FP64 SIMT products
   int64_t fast_launches = 0, tc_launches = 0;
   double* trace_user = nullptr;   // optional residual-trace sink of the next solves (twoace_set_trace)
@@ -537,8 +538,8 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
 
 static int launch_spectral(twoace_ctx* ctx, const std::vector<SpecTask>& tasks, int n, size_t& cursor) {
   if (tasks.empty()) return 0;
-  SpecDims dm;
-  dm.n = n; dm.maxm = 1; dm.dmax = 1;
+  SpecDims dm = {};
+  dm.n = n; dm.maxm = 1; dm.dmax = 1; dm.force_jacobi = ctx->opt_spectral_jacobi;
   for (const SpecTask& t : tasks) {
     dm.maxm = std::max(dm.maxm, t.m);
     dm.dmax = std::max(dm.dmax, t.m <= n ? t.m : n);
@@ -1661,6 +1662,7 @@ extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   else if (k == "dedup_nuclear_rerun") ctx->opt_dedup_nuclear = value ? 1 : 0;
   else if (k == "tensor") ctx->opt_tensor = value ? 1 : 0;
   else if (k == "cache_sinv") ctx->opt_cache_sinv = value ? 1 : 0;
+  else if (k == "spectral_jacobi") ctx->opt_spectral_jacobi = value ? 1 : 0;
   else FAIL(TWOACE_E_INVALID, "unknown option %s", key);
   return TWOACE_OK;
 }

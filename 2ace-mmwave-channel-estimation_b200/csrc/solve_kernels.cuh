@@ -6,6 +6,7 @@
 // fixed launch sequence with no round trips.
 #pragma once
 #include "fast_stage.cuh"
+#include "tridiag_eig.cuh"
 
 namespace twoace {
 
@@ -98,7 +99,7 @@ struct SpecTask {
   int* sweeps;         // optional
 };
 
-struct SpecDims { int n, maxm, dmax; size_t ws_stride; };
+struct SpecDims { int n, maxm, dmax; size_t ws_stride; int force_jacobi; };
 
 __host__ __device__ inline size_t spec_ws_elems(const SpecDims& d) {
   return (size_t)d.maxm * d.n + 2 * (size_t)d.dmax * d.dmax;
@@ -209,6 +210,14 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
       }
     }
     __syncthreads();
+    if (d > 96 && d <= TRI_DMAX && r <= TRI_RMAX && !dm.force_jacobi) {
+      // only the r leading eigenpairs are used (:550-552): tridiagonalisation + bisection + inverse iteration
+      const int rr = min(r, d);
+      top_eig_tridiag(G, d, rr, V, s2, (unsigned char*)bjS, red);
+      if (tid == 0 && tk.sweeps) *tk.sweeps = 0;
+      for (int c = tid; c < rr; c += NT) { s2[c] = fmax(0.0, s2[c]); ord[c] = c; }     // clamp (:550); already descending
+      __syncthreads();
+    } else {
     // large problems: block Jacobi (16x less memory traffic per sweep than element-wise rotations)
     const int sw = (d > 96) ? block_jacobi_heig(G, d, V, d, d, bjS, bjS + 1024, bjS + 2048, bjTab, 40)
                             : jacobi_heig(G, d, V, d, d, true, js, 60);
@@ -223,6 +232,7 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
       ord[rank] = i;
     }
     __syncthreads();
+    }
     if (gram) {   // Xs[:, c] = As' W[:, ord[c]]  (zero column when c >= m)
       gemm_tpo(n, m, min(r, d),
                [&](int i, int k) -> cd { cd a = tk.A.base[(size_t)rows_s[i] * n + k]; return cmk(a.x, -a.y); },

@@ -50,7 +50,7 @@ def _stage_case(codebook, M, trial=0):
     return A[tr], B[tr]
 
 
-@pytest.mark.parametrize("M", [36, 64, 121])
+@pytest.mark.parametrize("M", [36, 64, 121, 225, 256])
 def test_spectral_init_parity(codebook, gpu_ctx, M):
     from twoace_b200 import solvers as sv
     At, Bt = _stage_case(codebook, M)
@@ -61,11 +61,19 @@ def test_spectral_init_parity(codebook, gpu_ctx, M):
     assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-10
 
 
-def test_spectral_init_n_by_n_branch(codebook, gpu_ctx):
+@pytest.mark.parametrize("M", [361, 1024])
+@pytest.mark.parametrize("solver", ["tridiag", "jacobi"])
+def test_spectral_init_n_by_n_branch(codebook, gpu_ctx, M, solver):
+    """m_train > n = 256: eig of the n x n matrix As'As.  Both eigensolvers: the leading-eigenpair route
+    (csrc/tridiag_eig.cuh, the default for 96 < d <= 512) and the full block-Jacobi decomposition."""
     from twoace_b200 import solvers as sv
-    At, Bt = _stage_case(codebook, 361)     # m_train = 342 > n = 256
+    At, Bt = _stage_case(codebook, M)
     Xo = admm.spectral_initialize(At, Bt, 20)
-    Xg = sv.spectral_init_batch([At], [Bt], 20, gpu_ctx)[0]
+    gpu_ctx.set_option("spectral_jacobi", 1 if solver == "jacobi" else 0)
+    try:
+        Xg = sv.spectral_init_batch([At], [Bt], 20, gpu_ctx)[0]
+    finally:
+        gpu_ctx.set_option("spectral_jacobi", 0)
     assert rel(Xg @ Xg.conj().T, Xo @ Xo.conj().T) < 1e-9
 
 

@@ -5,8 +5,8 @@
 ``solvers``  mirror of the reference's MATLAB solver signatures over the C ABI
 """
 from . import entrypoints, harness, lib, parallel, solvers  # noqa: F401
-from .lib import NUCLEAR, V1, V2, V3, V4, V4_MULTI, Context, Params, PlOpts, SynthParams, TwoaceError  # noqa: F401
-from .solvers import (ADMM_v2, ADMM_v2_nuclear, MyPhaseLift, inferLowRank, inferLowRank_Nuclear,  # noqa: F401
+from .lib import MINL2, NUCLEAR, V1, V2, V3, V4, V4_MULTI, Context, Params, PlOpts, SynthParams, TwoaceError  # noqa: F401
+from .solvers import (ADMM_v2, ADMM_v2_nuclear, MyPhaseLift, inferLowRank, inferLowRank_Nuclear, inferMinL2,  # noqa: F401
                       inferLowRankV2, inferLowRankV3, inferLowRankV4,
                       inferLowRankV4_multi, phaselift_batch, phaselift_batch_codebook, solve_batch,
                       solve_batch_codebook)

@@ -14,6 +14,7 @@
 #include "phaselift.cuh"
 #include "metrics.cuh"
 #include "synth.cuh"
+#include "minl2.cuh"
 #include <thread>
 
 using namespace twoace;
@@ -440,6 +441,44 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
   return 0;
 }
 
+// InferADMM of inferMinL2.m (no low-rank variable): general kernel with a per-CTA global workspace
+static int launch_minl2(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n, size_t& cursor) {
+  if (tasks.empty()) return 0;
+  Minl2Dims dm = {};
+  dm.n = n; dm.maxm = 1; dm.maxr = 1;
+  for (const StageTask& t : tasks) { dm.maxm = std::max(dm.maxm, t.m); dm.maxr = std::max(dm.maxr, t.r); }
+  dm.ws_stride = (minl2_ws_elems(dm) + 15) / 16 * 16;
+  const size_t smem = minl2_smem_bytes(dm);
+  if (smem > SMEM_LIMIT) FAIL(TWOACE_E_UNSUPPORTED, "inferMinL2 stage kernel does not fit: %zu bytes of shared memory", smem);
+  int occ = 0;
+  CK(cudaFuncSetAttribute(minl2_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, minl2_stage_kernel, NT, smem));
+  if (occ < 1) FAIL(TWOACE_E_UNSUPPORTED, "inferMinL2 stage kernel does not fit: %zu bytes of shared memory", smem);
+  const int grid = std::max(1, std::min((int)tasks.size(), occ * ctx->num_sms));
+  int rc = ensure(ctx, ctx->ws, (size_t)grid * dm.ws_stride * sizeof(cd));
+  if (rc) return rc;
+  const StageTask* dt = nullptr;
+  rc = upload_tasks(ctx, tasks, cursor, &dt);
+  if (rc) return rc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  minl2_stage_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), prm, dm, (cd*)ctx->ws.p);
+  CK(cudaGetLastError());
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->stage_events.emplace_back(e0, e1);
+    char lb[160];
+    snprintf(lb, sizeof lb, "minl2_stage_kernel tasks %d grid %d maxm %d maxr %d", (int)tasks.size(), grid, dm.maxm, dm.maxr);
+    ctx->stage_labels.emplace_back(lb);
+  }
+  ctx->launches++;
+  return 0;
+}
+
 // Shared-memory geometry of the cluster kernel for an r = 20 task with m rows; false when it does not fit.
 template <int RL>
 static bool fast_dims(int m, bool nuc, bool tc, FastDims* out) {
@@ -458,6 +497,7 @@ static bool fast_dims(int m, bool nuc, bool tc, FastDims* out) {
 static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, const DevParams& prm, int n,
                         int tx, int rx, size_t& cursor) {
   if (tasks.empty()) return 0;
+  if (tasks.front().nuclear == 2) return launch_minl2(ctx, tasks, prm, n, cursor);     // a launch is all of one kind
   // groups: 0 = <10,2> tensor-core, 1 = <5,4> tensor-core, 2 = <10,2> SIMT, 3 = <5,4> SIMT, 4 = r = 1
   std::vector<StageTask> grp[5], gen, big, big1;
   bool nuc = false;
@@ -639,8 +679,11 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   // older solver versions (ADMM_v2.m:26-31): no rank-one rerun; V1 / V2 refine only when quality > 0.6; their
   // rank profile travels in StageTask.rank_one (2: inferLowRank.m, 3: inferLowRankV2.m -- identical to the V4
   // profile once ceil(0.7 sqrt(min(tx,rx))) > 2, i.e. from 9 antennas on)
-  const bool older = in.variant == TWOACE_V3 || in.variant == TWOACE_V2 || in.variant == TWOACE_V1;
-  const int refine_if_good = (in.variant == TWOACE_V2 || in.variant == TWOACE_V1) ? 1 : 0;
+  // inferMinL2.m (ADMM_v2.m:23, version 0): the same shell (train solve, held-out quality, refine only if quality > 0.6,
+  // roll-back) around a solver without the low-rank variable; train rows = ceil(0.95 m) (:34), rank from the 90 % rule
+  const bool minl2 = in.variant == TWOACE_MINL2;
+  const bool older = in.variant == TWOACE_V3 || in.variant == TWOACE_V2 || in.variant == TWOACE_V1 || minl2;
+  const int refine_if_good = (in.variant == TWOACE_V2 || in.variant == TWOACE_V1 || minl2) ? 1 : 0;
   const int prof = in.variant == TWOACE_V1 ? 2 : (in.variant == TWOACE_V2 && std::min(in.tx, in.rx) < 9) ? 3 : 0;
   const bool dense = in.dA != nullptr;
 
@@ -651,12 +694,13 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   for (int b = 0; b < nb; ++b) {
     const int m = in.m[b];
     if (m < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m);
-    mtr[b] = (int)std::floor((double)m * in.p.cc_frac);
+    mtr[b] = minl2 ? (int)std::ceil((double)m * 0.95) : (int)std::floor((double)m * in.p.cc_frac);
     mte[b] = m - mtr[b];
-    if (mtr[b] < 1 || mte[b] < 1) FAIL(TWOACE_E_INVALID, "instance %d: empty train or test split", b);
+    // (inferMinL2 with m <= 20 has an empty test set: quality = 1 - 0/0 = NaN, no refinement, as in MATLAB)
+    if (mtr[b] < 1 || (mte[b] < 1 && !minl2)) FAIL(TWOACE_E_INVALID, "instance %d: empty train or test split", b);
     // r = min([r m n]) (:12); versions 1-3 re-evaluate it inside inferLowRankImpl with m = m_train, BEFORE their
     // spectral init (inferLowRankV3.m:198-224), V4 / _multi / _Nuclear initialise outside with the full-m clamp
-    rb[b] = std::min(std::min((int)in.p.r, older ? mtr[b] : m), n);
+    rb[b] = std::min(std::min((int)in.p.r, (older && !minl2) ? mtr[b] : m), n);
     maxr = std::max(maxr, rb[b]);
     a_off[b + 1] = a_off[b] + (size_t)m * n;
     b_off[b + 1] = b_off[b] + m;
@@ -815,6 +859,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         s.B = in.dB + b_off[b]; s.brows = d_trainB + tr_off[b] + (size_t)t * mtr[b];
         s.bscale = &d_ctl[b].b_scale; s.m = mtr[b]; s.r = rb[b];
         s.Xs = d_Xs + (size_t)b * xstride; s.sweeps = nullptr;
+        s.r_out = minl2 ? &d_ctl[b].r_eff : nullptr;
       }
       rc = launch_spectral(ctx, st, n, cursor);
       if (rc) return rc;
@@ -829,7 +874,8 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.B = in.dB + b_off[b]; a.brows = d_trainB + tr_off[b] + (size_t)t * mtr[b];
         a.bscale = &d_ctl[b].b_scale; a.m = mtr[b]; a.r = rb[b];
         a.X0 = d_Xs + (size_t)b * xstride; a.Xout = d_Xa + (size_t)b * xstride; a.Yout = nullptr;
-        a.sbr = 1; a.rank_one = pass ? 1 : prof; a.nuclear = nuclear; a.rank_one_ptr = nullptr;
+        a.sbr = 1; a.rank_one = pass ? 1 : prof; a.nuclear = minl2 ? 2 : nuclear; a.rank_one_ptr = nullptr;
+        a.r_ptr = minl2 ? &d_ctl[b].r_eff : nullptr;
         a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
         a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass) * in.p.maxiter : nullptr;
@@ -844,7 +890,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         s2.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass + 1) * STAGE_SCAL;
         s2.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass + 1) * in.p.maxiter : nullptr;
         OrthoTask& o = ot[b];
-        o.X = d_Xa + (size_t)b * xstride; o.r = rb[b]; o.active = a.active; o.active_expect = 1;
+        o.X = d_Xa + (size_t)b * xstride; o.r = rb[b]; o.r_ptr = a.r_ptr; o.active = a.active; o.active_expect = 1;
         QualTask& q = qt[b];
         q.A = aview(b, d_testA + te_off[b] + (size_t)t * mte[b]);
         q.B = in.dB + b_off[b]; q.brows = d_testB + te_off[b] + (size_t)t * mte[b];
@@ -882,7 +928,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.A = aview(b, dense ? nullptr : d_fullA + b_off[b]);
       a.B = in.dB + b_off[b]; a.brows = nullptr; a.bscale = &d_ctl[b].b_scale;
       a.m = in.m[b]; a.r = 1; a.X0 = d_xmax + (size_t)b * n; a.Xout = d_xr + (size_t)b * n; a.Yout = d_yr + b_off[b];
-      a.sbr = 1; a.rank_one = prof; a.nuclear = nuclear; a.rank_one_ptr = older ? nullptr : &d_ctl[b].use_rank_one;
+      a.sbr = 1; a.rank_one = prof; a.nuclear = minl2 ? 2 : nuclear; a.rank_one_ptr = older ? nullptr : &d_ctl[b].use_rank_one;
       a.active = refine_if_good ? &d_ctl[b].refine_on : nullptr; a.active_expect = 1;
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
       a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + (nstage - 1)) * in.p.maxiter : nullptr;
@@ -942,13 +988,18 @@ static int host_back(twoace_ctx* ctx, int mem, void* host, const void* dev, size
   return 0;
 }
 
+// train rows per draw: floor(m cc_frac) (inferLowRankV4.m:36), ceil(0.95 m) for inferMinL2 (inferMinL2.m:34)
+static size_t train_rows(int variant, int m, double cc_frac) {
+  return variant == TWOACE_MINL2 ? (size_t)std::ceil((double)m * 0.95) : (size_t)std::floor((double)m * cc_frac);
+}
+
 static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, int rx, const int32_t* m,
                         const double* A, const int32_t* cb_rows, double row_scale, const double* B,
                         const int32_t* train_idx, const twoace_params* params, double* X, double* Y,
                         double* quality, double* info, double* stage_words) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->err.clear();
-  if (variant < TWOACE_V4 || variant > TWOACE_V1) FAIL(TWOACE_E_INVALID, "unknown variant %d", variant);
+  if (variant < TWOACE_V4 || variant > TWOACE_MINL2) FAIL(TWOACE_E_INVALID, "unknown variant %d", variant);
   if (nb < 0 || !m || !B || !train_idx || !X || !Y || !quality) FAIL(TWOACE_E_INVALID, "null argument");
   if (!A && !cb_rows) FAIL(TWOACE_E_INVALID, "neither dense A nor codebook rows given");
   if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
@@ -969,7 +1020,7 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
   for (int b = 0; b < nb; ++b) {
     if (m[b] < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m[b]);
     sum_m += m[b];
-    sum_tr += (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+    sum_tr += (size_t)T * train_rows(variant, m[b], p.cc_frac);
   }
   Staging st;
   const void *dA = nullptr, *dB = nullptr;
@@ -1009,7 +1060,7 @@ static int solve_common(twoace_ctx* ctx, int variant, int mem, int nb, int tx, i
     if (rc) return rc;
     for (int b = b0; b < b0 + cnt; ++b) {
       ao += (size_t)m[b] * n; bo += m[b];
-      to += (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+      to += (size_t)T * train_rows(variant, m[b], p.cc_frac);
     }
   }
   rc = host_back(ctx, mem, X, dX, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
@@ -1040,7 +1091,7 @@ static int solve_multi(twoace_ctx* ctx, int variant, int mem, int nb, int tx, in
   const size_t n = (size_t)tx * rx;
   for (int b = 0; b < nb; ++b) if (m[b] < 2) FAIL(TWOACE_E_INVALID, "instance %d: m = %d (need m >= 2)", b, m[b]);
   std::vector<size_t> tr_off(nb + 1, 0);
-  for (int b = 0; b < nb; ++b) tr_off[b + 1] = tr_off[b] + (size_t)T * (size_t)std::floor((double)m[b] * p.cc_frac);
+  for (int b = 0; b < nb; ++b) tr_off[b + 1] = tr_off[b] + (size_t)T * train_rows(variant, m[b], p.cc_frac);
   const auto sl = split_batch(m, nb, 1 + (int)ctx->peers.size());
   return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
     return solve_common(c, variant, mem, s.b1 - s.b0, tx, rx, m + s.b0, A ? A + 2 * s.rows0 * n : nullptr,
@@ -1236,7 +1287,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     a.B = (const double*)dB + b_off[b]; a.brows = nullptr; a.bscale = d_one;
     a.m = m[b]; a.r = r; a.X0 = (const cd*)dX0 + (size_t)b * n * r;
     a.Xout = (cd*)dX + (size_t)b * n * rout; a.Yout = (cd*)dY + b_off[b] * rout;
-    a.sbr = scale_by_row ? 1 : 0; a.rank_one = use_rank_one ? 1 : 0; a.nuclear = nuclear ? 1 : 0;
+    a.sbr = scale_by_row ? 1 : 0; a.rank_one = use_rank_one ? 1 : 0; a.nuclear = nuclear == 2 ? 2 : (nuclear ? 1 : 0);   // 2: the inferMinL2.m iteration (no low-rank variable)
     a.rank_one_ptr = nullptr; a.active = nullptr; a.active_expect = 1;
     a.scal = dW ? (double*)dW + (size_t)b * STAGE_SCAL : nullptr;
     a.state = dSt ? (cd*)dSt + st_off[b] : nullptr;

@@ -28,6 +28,7 @@ struct InstCtl {
   double c_scale;      // quantised codebooks: A_eff = c_scale * u(code)
   int quant;           // 1 when every entry of A is c * {1, j, -1, -j}
   int refine_on;       // 0 when the refine stage is skipped (inferLowRankV2.m:47: only if quality > 0.6)
+  int r_eff;           // inferMinL2.m:181-185: columns kept by the 90 %-energy rule of its spectral initialisation
 };
 
 // ---- pre-processing ----------------------------------------------------------------------
@@ -97,6 +98,8 @@ struct SpecTask {
   int m, r;
   cd* Xs;              // n x r out
   int* sweeps;         // optional
+  int* r_out;          // optional: inferMinL2.m:181-185 -- if the r leading eigenvalues hold >= 90 % of the trace,
+                       // r_out = max(3, smallest k whose k leading eigenvalues hold 90 %), capped by m and n; else r
 };
 
 struct SpecDims { int n, maxm, dmax; size_t ws_stride; int force_jacobi; };
@@ -210,6 +213,13 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
       }
     }
     __syncthreads();
+    double trace_g = 0.0;
+    if (tk.r_out != nullptr) {     // sum of all eigenvalues (inferMinL2.m:181: sum(s2)); clamped negatives are rounding noise
+      double v[1] = {0.0};
+      for (int i = tid; i < d; i += NT) v[0] += G[i + (size_t)d * i].x;
+      block_sum<1>(v, red);
+      trace_g = v[0];
+    }
     if (d > 96 && d <= TRI_DMAX && r <= TRI_RMAX && !dm.force_jacobi) {
       // only the r leading eigenpairs are used (:550-552): tridiagonalisation + bisection + inverse iteration
       const int rr = min(r, d);
@@ -233,6 +243,19 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
     }
     __syncthreads();
     }
+    if (tk.r_out != nullptr && tid == 0) {
+      const int rr = min(r, d);
+      double head = 0.0;
+      for (int c = 0; c < rr; ++c) head += s2[ord[c]];
+      int re = r;
+      if (head >= trace_g * 0.9) {
+        double cum = 0.0;
+        int k = rr;
+        for (int c = 0; c < rr; ++c) { cum += s2[ord[c]]; if (cum >= trace_g * 0.9) { k = c + 1; break; } }
+        re = min(min(max(k, 3), m), n);
+      }
+      *tk.r_out = re;
+    }
     if (gram) {   // Xs[:, c] = As' W[:, ord[c]]  (zero column when c >= m)
       gemm_tpo(n, m, min(r, d),
                [&](int i, int k) -> cd { cd a = tk.A.base[(size_t)rows_s[i] * n + k]; return cmk(a.x, -a.y); },
@@ -254,6 +277,7 @@ spectral_init_kernel(const SpecTask* __restrict__ tasks, int ntasks, SpecDims dm
 struct OrthoTask {
   cd* X;               // n x r, in place
   int r;
+  const int* r_ptr;    // optional device override of r
   const int* active; int active_expect;
 };
 
@@ -282,7 +306,7 @@ ortho_kernel(const OrthoTask* __restrict__ tasks, int ntasks, int n, int rmax) {
   for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
     const OrthoTask tk = tasks[t];
     if (tk.active != nullptr && *tk.active != tk.active_expect) continue;
-    const int r = tk.r;
+    const int r = tk.r_ptr ? *tk.r_ptr : tk.r;
     const int pitch = r | 1;
     const int KT = min(64, (NT * RCH) / pitch);
     for (int idx = tid; idx < r * r; idx += NT) G[idx] = cmk(0.0, 0.0);

@@ -28,10 +28,11 @@ struct StageTask {
   const int* brows;
   const double* bscale; // device scalar (1/B_norm)
   int m, r;             // rows of A_eff, columns of X0
+  const int* r_ptr;     // optional device override of r (inferMinL2.m:181-185: rank chosen by the spectral initialisation)
   const double2* X0;    // n x r column-major
   double2* Xout;        // n x (sbr ? r : 1)
   double2* Yout;        // m x (sbr ? r : 1)
-  int sbr, rank_one, nuclear;
+  int sbr, rank_one, nuclear;   // nuclear: 0 V4 ArgMinZ, 1 SVT ArgMinZ, 2 no low-rank variable (inferMinL2.m)
   const int* rank_one_ptr;  // optional device override of rank_one (decided by an earlier kernel)
   const int* active;    // device flag (nullptr = always active); inactive tasks return immediately
   int active_expect;    // task runs iff *active == active_expect

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtwoace.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-V4, V4_MULTI, NUCLEAR, V3, V2, V1 = 0, 1, 2, 3, 4, 5
+V4, V4_MULTI, NUCLEAR, V3, V2, V1, MINL2 = 0, 1, 2, 3, 4, 5, 6
 INFO_WORDS = 16
 STAGE_WORDS = 16
 PL_INFO_WORDS = 16

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import lib as _lib
-from .lib import NUCLEAR, V1, V2, V3, V4, V4_MULTI, Params, PlOpts
+from .lib import MINL2, NUCLEAR, V1, V2, V3, V4, V4_MULTI, Params, PlOpts
 
 __all__ = ["inferLowRankV4", "inferLowRankV4_multi", "inferLowRank_Nuclear", "ADMM_v2", "ADMM_v2_nuclear",
            "solve_batch", "solve_batch_codebook", "infer_admm_batch", "spectral_init_batch", "BatchResult",
@@ -49,7 +49,12 @@ class BatchResult:
     stage_words: np.ndarray  # [nb, 4T+1, 12]
 
 
-def _concat_inputs(A_list, B_list, train_idx_list, ntrial, cc_frac, n):
+def train_rows(variant: int, m: int, cc_frac: float) -> int:
+    """Entries of one train draw: floor(m*cc_frac) (inferLowRankV4.m:36); ceil(0.95 m) for inferMinL2 (inferMinL2.m:34)."""
+    return int(math.ceil(m * 0.95)) if variant == MINL2 else int(math.floor(m * cc_frac))
+
+
+def _concat_inputs(A_list, B_list, train_idx_list, ntrial, cc_frac, n, variant=V4):
     nb = len(A_list)
     m = np.array([np.shape(a)[0] for a in A_list], dtype=np.int32)
     for a in A_list:
@@ -61,9 +66,9 @@ def _concat_inputs(A_list, B_list, train_idx_list, ntrial, cc_frac, n):
     tr = []
     for b in range(nb):
         t = np.asarray(train_idx_list[b], dtype=np.int32).reshape(ntrial, -1)
-        k = int(math.floor(int(m[b]) * cc_frac))
+        k = train_rows(variant, int(m[b]), cc_frac)
         if t.shape[1] != k:
-            raise ValueError(f"instance {b}: train_idx needs floor(m*cc_frac) = {k} entries per draw, got {t.shape[1]}")
+            raise ValueError(f"instance {b}: train_idx needs {k} entries per draw, got {t.shape[1]}")
         tr.append(t.reshape(-1))
     T = np.concatenate(tr) if nb else np.zeros(0, np.int32)
     return m, np.ascontiguousarray(A), np.ascontiguousarray(B), np.ascontiguousarray(T.astype(np.int32))
@@ -83,7 +88,7 @@ def solve_batch(variant: int, A_list, B_list, tx: int, rx: int, train_idx_list, 
     p = params or Params.default()
     nb, n = len(A_list), tx * rx
     ntrial = 3 if variant == V4_MULTI else 1
-    m, A, B, T = _concat_inputs(A_list, B_list, train_idx_list, ntrial, p.cc_frac, n)
+    m, A, B, T = _concat_inputs(A_list, B_list, train_idx_list, ntrial, p.cc_frac, n, variant)
     X = np.empty(nb * n, np.complex128)
     Y = np.empty(int(m.sum()), np.complex128)
     q = np.empty(nb, np.float64)
@@ -107,7 +112,7 @@ def solve_batch_codebook(variant: int, rows_list, row_scale: float, B_list, tx: 
     tr = []
     for b in range(nb):
         t = np.asarray(train_idx_list[b], dtype=np.int32).reshape(ntrial, -1)
-        k = int(math.floor(int(m[b]) * p.cc_frac))
+        k = train_rows(variant, int(m[b]), p.cc_frac)
         if t.shape[1] != k:
             raise ValueError(f"instance {b}: train_idx needs {k} entries per draw, got {t.shape[1]}")
         tr.append(t.reshape(-1))
@@ -308,24 +313,51 @@ def inferLowRank(A, B, tx, rx, lambda_=0.0, r=20, tol_rel=1e-4, tol_abs=1e-8, ma
                    train_idx, rng, ctx)
 
 
+def inferMinL2(A, B, lambda_=0.0, r=20, tol_rel=1e-4, tol_abs=1e-8, maxiter=500, *, train_idx=None, rng=None, ctx=None):
+    """[X, Y, quality] = inferMinL2(A, B, lambda, r, tol_rel, tol_abs, maxiter)  (ADMM_v2/inferMinL2.m:1; ADMM_v2.m:23).
+    ``train_idx``: the randsample(m, ceil(m*0.95)) draw of :34, 0-based (drawn from ``rng`` when absent)."""
+    A = np.asarray(A, dtype=np.complex128)
+    m, n = A.shape
+    tx = next((t for t in (16, 32, 8, 4) if n % t == 0), None)      # only n = tx * rx matters to this solver
+    if tx is None:
+        raise ValueError("inferMinL2 through this library needs n divisible by 4")
+    p = _params(lambda_, r, 1e-3, 1.03, 0.95, tol_rel, tol_abs, maxiter)
+    if train_idx is None:
+        train_idx = (rng or np.random.default_rng()).permutation(m)[:train_rows(MINL2, m, 0.95)].astype(np.int32)
+    res = solve_batch(MINL2, [A], [B], tx, n // tx, [train_idx], p, ctx)
+    return res.X[0], res.Y[0], float(res.quality[0])
+
+
 def ADMM_v2(measurements, FW, TX, RX, version, *, tree="main", train_idx=None, rng=None, ctx=None):
     """[X, Y, converged] = ADMM_v2(measurements, FW, TX, RX, version).  As in the reference the third
-    output is really ``quality`` (ADMM_v2.m:31-32 vs inferLowRankV4.m:1).  Version 0 (inferMinL2) and the
-    version >= 5 loop (which passes lambda != 0) are not part of this build."""
+    output is really ``quality`` (ADMM_v2.m:31-32 vs inferLowRankV4.m:1).  Version map: main/.../ADMM_v2.m:22-31
+    (1 inferLowRank, 2 inferLowRankV2, 3 inferLowRankV3, 4 inferLowRankV4_multi) and
+    Numerical_Simulation/.../ADMM_v2.m:22-29 (1 inferLowRank, 2 inferLowRankV3, 3 inferLowRankV4).  Version 0
+    (inferMinL2) is served by ``inferMinL2``; the trailing else-loop (main :33-43, NS :30-41) calls inferLowRankV2 with
+    lambda = rz + 2 != 0, the eigen-path of ArgMinX that no caller of the reference reaches -- not built."""
     B = np.asarray(measurements, dtype=np.float64).reshape(-1)
-    if tree == "main" and version == 4:
-        return inferLowRankV4_multi(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
-    if tree == "main" and version in (1, 2, 3):                                         # ADMM_v2.m:26-31
-        fn = {1: inferLowRank, 2: inferLowRankV2, 3: inferLowRankV3}[version]
-        return fn(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
-    if tree == "ns" and version == 3:
-        return inferLowRankV4(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
-    raise NotImplementedError(f"ADMM_v2 version {version} (tree {tree!r}) is outside the accelerated hot path")
+    kw = dict(train_idx=train_idx, rng=rng, ctx=ctx)
+    if version == 0:
+        return inferMinL2(FW, B, train_idx=train_idx, rng=rng, ctx=ctx)
+    if tree == "main":
+        table = {1: inferLowRank, 2: inferLowRankV2, 3: inferLowRankV3, 4: inferLowRankV4_multi}
+    elif tree == "ns":
+        table = {1: inferLowRank, 2: inferLowRankV3, 3: inferLowRankV4}
+    else:
+        raise ValueError(f"unknown tree {tree!r} (main | ns)")
+    if version in table:
+        return table[version](FW, B, TX, RX, **kw)
+    raise NotImplementedError(f"ADMM_v2 version {version} (tree {tree!r}): the lambda != 0 retry loop is dead code in the "
+                              "reference and outside this build")
 
 
 def ADMM_v2_nuclear(measurements, FW, TX, RX, version, *, train_idx=None, rng=None, ctx=None):
-    """ADMM_v2_nuclear.m: version 4 -> inferLowRank_Nuclear."""
+    """main/src/my_recovery_algorithms/ADMM_v2_nuclear.m:22-32: versions 1-3 as ADMM_v2, 4 -> inferLowRank_Nuclear."""
     B = np.asarray(measurements, dtype=np.float64).reshape(-1)
-    if version == 4:
-        return inferLowRank_Nuclear(FW, B, TX, RX, train_idx=train_idx, rng=rng, ctx=ctx)
-    raise NotImplementedError(f"ADMM_v2_nuclear version {version} is outside the accelerated hot path")
+    kw = dict(train_idx=train_idx, rng=rng, ctx=ctx)
+    if version == 0:
+        return inferMinL2(FW, B, train_idx=train_idx, rng=rng, ctx=ctx)
+    table = {1: inferLowRank, 2: inferLowRankV2, 3: inferLowRankV3, 4: inferLowRank_Nuclear}
+    if version in table:
+        return table[version](FW, B, TX, RX, **kw)
+    raise NotImplementedError(f"ADMM_v2_nuclear version {version}: the lambda != 0 retry loop is outside this build")

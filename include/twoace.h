@@ -48,7 +48,11 @@ enum {
   TWOACE_NUCLEAR = 2,   /* inferLowRank_Nuclear.m  (main ADMM_v2_nuclear.m version 4) */
   TWOACE_V3 = 3,        /* inferLowRankV3.m        (main ADMM_v2.m version 3): V4 without the rank-one rerun */
   TWOACE_V2 = 4,        /* inferLowRankV2.m        (main ADMM_v2.m version 2): refine only if quality > 0.6  */
-  TWOACE_V1 = 5         /* inferLowRank.m          (main ADMM_v2.m version 1): single-stage rank profile     */
+  TWOACE_V1 = 5,        /* inferLowRank.m          (main ADMM_v2.m version 1): single-stage rank profile     */
+  TWOACE_MINL2 = 6      /* inferMinL2.m            (ADMM_v2.m version 0): no low-rank variable, X = pinv(A)(Y - M/mu).
+                         * [X,Y,quality] = inferMinL2(A,B,lambda,r,tol_rel,tol_abs,maxiter): mu0, rho and cc_frac of
+                         * twoace_params are ignored (1e-3, 1.03, 0.95 are hard-wired, inferMinL2.m:34,269-270), the
+                         * train draw has ceil(0.95 m) entries (:34), tx / rx only give n = tx * rx */
 };
 
 /* Optional positional arguments of inferLowRankV4.m:2-9 (defaults in twoace_default_params). */

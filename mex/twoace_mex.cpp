@@ -2,7 +2,8 @@
 // Same base name on the MATLAB path shadows main/src/my_recovery_algorithms/ADMM_v2/inferLowRankV4.m.
 // Build three times with -DTWOACE_VARIANT=0|1|2 and -output inferLowRankV4 | inferLowRankV4_multi |
 // inferLowRank_Nuclear:
-//   mex -R2018a -DTWOACE_VARIANT=1 -output inferLowRankV4_multi mex/twoace_mex.cpp -Iinclude -L<dir> -ltwoace
+//   mex -R2018a -DTWOACE_HAVE_MEX -DTWOACE_VARIANT=1 -output inferLowRankV4_multi mex/twoace_mex.cpp -Iinclude -L<dir> -ltwoace
+// (without -DTWOACE_HAVE_MEX the file compiles to an empty object: the guard keeps the tree buildable without mex.h)
 // Not compiled in this repository's CI: mex.h / libmex are absent (no MATLAB in the image).  The code only
 // uses the documented interleaved-complex MEX API and the C ABI of include/twoace.h.
 #ifdef TWOACE_HAVE_MEX

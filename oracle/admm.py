@@ -534,12 +534,145 @@ def infer_low_rank_v4_multi(A, B, tx, rx, params: Params | None = None, *, train
     return X.reshape(-1) * s, Y.reshape(-1) * s, quality
 
 
+# ------------------------------------------------------------------------------------------------
+# inferMinL2.m (ADMM_v2.m:23, version 0): the same train / quality / refine shell around a plain
+# least-squares phase retrieval -- no low-rank variable Z: X = pinv(A) (Y - M/mu)
+def infer_admm_minl2(A, B, X0, scale_by_row, lam, tol_rel, tol_abs, maxiter, trace: StageTrace | None = None,
+                     snapshot_iters=None):
+    """inferMinL2.m:227-346 (InferADMM of that file) with lambda = 0: U = pinv(A) (:235-237)."""
+    if lam != 0:
+        raise NotImplementedError("lambda != 0 (eigen-path, inferMinL2.m:238-241) is dead in the reference")
+    A = np.asarray(A, dtype=np.complex128)
+    B = np.asarray(B, dtype=np.float64).reshape(-1)
+    X0 = np.asarray(X0, dtype=np.complex128)
+    if X0.ndim == 1:
+        X0 = X0[:, None]
+    m, n = A.shape
+    r = X0.shape[1]
+    U = np.linalg.pinv(A)                                       # :236
+    X = X0.copy()
+    AX = A @ X                                                  # :250
+    normB = np.linalg.norm(B)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if scale_by_row:
+            X = X * (normB / _fro(AX))                          # :252
+        else:
+            X = X * (normB / np.sqrt(np.sum(np.abs(AX) ** 2, axis=0)))[None, :]     # :254-256
+    AX = A @ X
+    Y = normalize_rows(AX, B, scale_by_row)                     # :262
+    AtY = A.conj().T @ Y
+    M = np.zeros((m, r), dtype=np.complex128)
+    mu, rho = 0.001, 1.03                                       # :269-270
+    opt_obj, last_res = np.inf, np.inf
+    opt_X = opt_Y = None
+    converged = False
+    it = 0
+    opt_iter, opt_col, bumps = -1, -1, 0
+    for it in range(1, maxiter + 1):
+        Y0, AtY0 = Y, AtY
+        X = U @ (Y - M / mu)                                    # :282, :350
+        AX = A @ X
+        Y = argmin_y(AX, B, M, mu, scale_by_row)                # :286
+        AtY = A.conj().T @ Y
+        J_M = AX - Y
+        M = M + mu * J_M                                        # :291-292
+        if scale_by_row:                                        # :296-312
+            obj = np.linalg.norm(np.sqrt(np.sum(np.abs(AX) ** 2, axis=1)) - B)
+            if obj < opt_obj:
+                opt_obj, opt_X, opt_Y, opt_iter, opt_col = obj, X.copy(), Y.copy(), it, -1
+        else:
+            objs = np.sqrt(np.sum((np.abs(AX) - B[:, None]) ** 2, axis=0))
+            obj, j = _min_skip_nan(objs)
+            if obj < opt_obj:
+                opt_obj, opt_X, opt_Y, opt_iter, opt_col = obj, X[:, j:j + 1].copy(), Y[:, j:j + 1].copy(), it, j
+        res_prim = _fro(J_M)                                    # :316-325
+        res_dual = mu * _fro(AtY - AtY0)
+        res_comb = math.sqrt(res_prim ** 2 + _fro(Y - Y0) ** 2)
+        nAX, nY = _fro(AX), _fro(Y)
+        th_prim = tol_abs * math.sqrt(m * r) + tol_rel * max(nAX, nY)
+        th_dual = tol_abs * math.sqrt(n * r) + tol_rel * _fro(AtY)
+        th_comb = tol_abs * math.sqrt(m * r * 2) + tol_rel * math.sqrt(max(nAX, nY) ** 2 + nY ** 2)
+        if snapshot_iters is not None and it in snapshot_iters:
+            snapshot_iters[it] = dict(X=X.copy(), Y=Y.copy(), M=M.copy())
+        if (res_prim < th_prim and res_dual < th_dual) or (res_comb < th_comb):
+            converged = True
+            break
+        if res_comb > last_res * 0.9:                           # :332-334
+            mu *= rho
+            bumps += 1
+        last_res = res_comb
+    if trace is not None:
+        trace.iters, trace.converged, trace.mu = it, converged, mu
+        trace.opt_iter, trace.opt_col, trace.n_mu_bumps = opt_iter, opt_col, bumps
+    if opt_X is None:                                           # every objective NaN: MATLAB errors on opt_X undefined
+        opt_X = np.full((n, r if scale_by_row else 1), np.nan, dtype=np.complex128)
+        opt_Y = np.full((m, r if scale_by_row else 1), np.nan, dtype=np.complex128)
+    return opt_X, opt_Y, converged
+
+
+def spectral_initialize_minl2(A, B, r):
+    """inferMinL2.m:163-196: SpectralInitialize plus the 90 %-energy rank rule (:181-185, applied twice: idempotent)."""
+    A = np.asarray(A, dtype=np.complex128)
+    B = np.asarray(B, dtype=np.float64).reshape(-1)
+    m, n = A.shape
+    As = A.copy()
+    an = np.sqrt(np.sum(np.abs(A) ** 2, axis=1))
+    nz = an != 0
+    As[nz, :] = A[nz, :] * (B[nz] / an[nz])[:, None]
+    s2, idx, V = _eigh_desc(As.conj().T @ As)
+    for _ in range(2):
+        if np.sum(s2[:r]) >= np.sum(s2) * 0.9:
+            k = int(np.nonzero(np.cumsum(s2) >= np.sum(s2) * 0.9)[0][0]) + 1
+            r = min(max(k, 3), m, n)
+    return V[:, idx[:r]] * np.sqrt(s2[:r])[None, :]
+
+
+def infer_min_l2(A, B, lam=0.0, r=20, tol_rel=1e-4, tol_abs=1e-8, maxiter=500, *, train_idx, info: SolveInfo | None = None):
+    """[X, Y, quality] = inferMinL2(A, B, lambda, r, tol_rel, tol_abs, maxiter)  (inferMinL2.m:1-66).
+    ``train_idx``: the randsample(m, ceil(m*0.95)) draw of :34 (0-based)."""
+    info = info if info is not None else SolveInfo()
+    A = np.asarray(A, dtype=np.complex128)
+    m, n = A.shape
+    r = min(r, m, n)                                            # :9
+    A, B, A_norm, B_norm = _preprocess(A, B, tol_abs)           # :17-28
+    train_idx = np.asarray(train_idx, dtype=np.int64)
+    assert train_idx.size == math.ceil(m * 0.95)
+    test_idx = test_index_set(m, train_idx)
+    A_train, B_train = A[train_idx, :], B[train_idx]
+    # inferMinL2Impl (:68-225)
+    X = spectral_initialize_minl2(A_train, B_train, r)
+    ta, tb = StageTrace(), StageTrace()
+    X, Y, _ = infer_admm_minl2(A_train, B_train, X, True, lam, tol_rel, tol_abs, maxiter, ta)
+    G = X.conj().T @ X                                          # :219-220  [Vx,Dx] = eig(X'*X); X = X*Vx
+    _, Vx = np.linalg.eigh(0.5 * (G + G.conj().T))
+    X = X @ Vx
+    X, Y, _ = infer_admm_minl2(A_train, B_train, X, False, lam, tol_rel, tol_abs, maxiter, tb)
+    info.traces += [ta, tb]
+    quality = quality_score(A[test_idx, :], B[test_idx], X) if test_idx.size else float("nan")   # :42 (0/0 -> NaN)
+    info.quality = quality
+    if quality > 0.6:                                           # :47-58
+        X0, Y0 = X, Y
+        tr = StageTrace()
+        X, Y, _ = infer_admm_minl2(A, B, X0, True, lam, tol_rel, tol_abs, maxiter, tr)
+        info.traces.append(tr)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            similarity = float(np.abs(np.vdot(X0, X)) / np.linalg.norm(X0) / np.linalg.norm(X))
+        info.similarity = similarity
+        if similarity < 0.6:
+            X, Y = X0, Y0
+            info.rolled_back = True
+    s = B_norm / A_norm
+    return X.reshape(-1) * s, Y.reshape(-1) * s, quality
+
+
 def admm_v2(measurements, FW, TX, RX, version, *, train_idx, tree="main", params: Params | None = None,
             info: SolveInfo | None = None):
     """Version switch.  ``tree``: 'main' (ADMM_v2.m:22-45), 'main_nuclear' (ADMM_v2_nuclear.m:32)
     or 'ns' (Numerical_Simulation/.../ADMM_v2.m:22-41).  Only the V4-family rows of SURVEY §2.2
     are on the hot path; the others raise NotImplementedError (scope row §8f-4)."""
     B = np.asarray(measurements, dtype=np.float64).reshape(-1)
+    if version == 0:
+        return infer_min_l2(FW, B, train_idx=train_idx, info=info)
     if tree == "main" and version == 4:
         return infer_low_rank_v4_multi(FW, B, TX, RX, params, train_idx=train_idx, info=info)
     if tree == "main" and version in (1, 2, 3):

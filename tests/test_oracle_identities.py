@@ -197,3 +197,35 @@ def test_older_version_profiles_and_flow():
     assert q2 == q3b
     if not q2 > 0.6:
         assert Y2.shape == (38,) and Y3b.shape == (m,)
+
+
+def test_minl2_oracle_properties():
+    """inferMinL2.m restatement: stationarity for m <= n (A pinv(A) = I), the 90 % rank rule, and descent of the
+    measurement misfit for m > n."""
+    import math
+    rng = np.random.default_rng(5)
+    n = 32
+    # m <= n: one iteration, X = pinv(A) normalize_rows(A X0)
+    A = (rng.standard_normal((20, n)) + 1j * rng.standard_normal((20, n))) / np.sqrt(2)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    B = np.abs(A @ x)
+    X0 = rng.standard_normal((n, 4)) + 1j * rng.standard_normal((n, 4))
+    tr = admm.StageTrace()
+    X, Y, conv = admm.infer_admm_minl2(A, B, X0, True, 0.0, 1e-4, 1e-8, 500, tr)
+    assert tr.iters == 1 and conv
+    assert np.allclose(A @ X, Y, atol=1e-10)
+    assert np.allclose(np.sqrt(np.sum(np.abs(Y) ** 2, axis=1)), B, atol=1e-12)
+    # rank rule (:181-185): 12 rows -> 12 nonzero eigenvalues, the r = 12 leading ones hold everything, so the rule
+    # fires and keeps the smallest head with 90 % of the energy
+    A12 = (rng.standard_normal((12, n)) + 1j * rng.standard_normal((12, n))) / np.sqrt(2)
+    Xs = admm.spectral_initialize_minl2(A12, np.abs(A12 @ x), 12)
+    assert 3 <= Xs.shape[1] < 12
+    A = (rng.standard_normal((300, n)) + 1j * rng.standard_normal((300, n))) / np.sqrt(2)
+    B = np.abs(A @ x)
+    assert admm.spectral_initialize_minl2(A, B, 20).shape[1] == 20       # flat spectrum: the rule does not fire
+    # m > n: the solver fits the magnitudes far better than the start point and recovers x up to a global phase
+    tr_idx = rng.permutation(300)[:math.ceil(300 * 0.95)]
+    Xh, _, q = admm.infer_min_l2(A, B, train_idx=tr_idx)
+    assert q > 0.9
+    c = np.vdot(Xh, x) / np.vdot(Xh, Xh)
+    assert np.linalg.norm(x - c * Xh) / np.linalg.norm(x) < 1e-2

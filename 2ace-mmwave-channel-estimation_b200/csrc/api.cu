@@ -1632,6 +1632,70 @@ extern "C" int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace
   });
 }
 
+static int angle_single(twoace_ctx* ctx, int mem, int nb, int nt, int nr, int L, int nqt, int nqr,
+                        double searching_area, double wavelength, double spacing, const double* X_est,
+                        const double* angles_true, double* out) {
+  if (!ctx) return TWOACE_E_INVALID;
+  ctx->err.clear();
+  if (nb < 0 || !X_est || !angles_true || !out) FAIL(TWOACE_E_INVALID, "null argument");
+  if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
+  if (nt < 1 || nr < 1 || nt > MET_DMAX || nr > MET_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "angle metrics: nt, nr must be in 1..%d", MET_DMAX);
+  if (L < 1 || L > ANG_LMAX) FAIL(TWOACE_E_INVALID, "L must be in [1,%d]", ANG_LMAX);
+  if (nqt < 1 || nqr < 1 || nqt > 4096 || nqr > 4096) FAIL(TWOACE_E_INVALID, "grid sizes must be in [1,4096]");
+  if (!(wavelength > 0.0) || !(spacing > 0.0) || !(searching_area > 0.0 && searching_area <= 180.0)) FAIL(TWOACE_E_INVALID, "bad array geometry");
+  if (nb == 0) return TWOACE_OK;
+  CK(cudaSetDevice(ctx->device));
+  AngDims dm = {};
+  dm.nt = nt; dm.nr = nr; dm.L = L; dm.nqt = nqt; dm.nqr = nqr;
+  dm.kph = 2.0 * 3.14159265358979323846 * spacing / wavelength;
+  // Sparse_Channel_Formulation.m:120-135: nearest grid point (first minimum) of the two ends of the searching area
+  auto nearest = [&](int nq, double x) {
+    int pos = 0;
+    double best = INFINITY;
+    for (int q = 0; q < nq; ++q) { const double e = std::fabs(dm.kph * (-1.0 + 2.0 * q / (double)nq) - x); if (e < best) { best = e; pos = q; } }
+    return pos;
+  };
+  const double lo = dm.kph * std::sin(-searching_area / 2.0 * 3.14159265358979323846 / 180.0);
+  const double hi = dm.kph * std::sin(searching_area / 2.0 * 3.14159265358979323846 / 180.0);
+  dm.u0 = nearest(nqt, lo); dm.u1 = nearest(nqt, hi); dm.v0 = nearest(nqr, lo); dm.v1 = nearest(nqr, hi);
+  const int nu = dm.u1 - dm.u0 + 1, nv = dm.v1 - dm.v0 + 1;
+  if ((size_t)nu * nv < (size_t)L) FAIL(TWOACE_E_INVALID, "the searching area holds fewer than L grid points");
+  dm.ws_stride = ((size_t)2 * nv * nt + (size_t)nv * nu + 15) / 16 * 16;
+  const int grid = std::min(nb, 4 * ctx->num_sms);
+  int rc = ensure(ctx, ctx->ws, (size_t)grid * dm.ws_stride * sizeof(double));
+  if (rc) return rc;
+  const size_t n = (size_t)nt * nr;
+  Staging st;
+  const void *dE = nullptr, *dA = nullptr;
+  void* dO = nullptr;
+  rc = dev_in(ctx, st, mem, X_est, (size_t)nb * n * sizeof(cd), &dE); if (rc) return rc;
+  rc = dev_in(ctx, st, mem, angles_true, (size_t)nb * 2 * L * sizeof(double), &dA); if (rc) return rc;
+  rc = dev_out(ctx, st, mem, out, (size_t)nb * ANG_WORDS * sizeof(double), &dO); if (rc) return rc;
+  angle_metrics_kernel<<<grid, NT, 0, ctx->stream>>>((const cd*)dE, (const double*)dA, nb, dm, (double*)dO, (double*)ctx->ws.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  rc = host_back(ctx, mem, out, dO, (size_t)nb * ANG_WORDS * sizeof(double)); if (rc) return rc;
+  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return TWOACE_OK;
+}
+
+extern "C" int twoace_angle_metrics_batch(twoace_ctx* ctx, int mem, int nb, int nt, int nr, int L, int nqt, int nqr,
+                                          double searching_area, double wavelength, double spacing, const double* X_est,
+                                          const double* angles_true, double* out) {
+  if (!ctx || ctx->peers.empty() || nb < 2)
+    return angle_single(ctx, mem, nb, nt, nr, L, nqt, nqr, searching_area, wavelength, spacing, X_est, angles_true, out);
+  ctx->err.clear();
+  int rc = multi_guard(ctx, mem);
+  if (rc) return rc;
+  if (!X_est || !angles_true || !out || L < 1) FAIL(TWOACE_E_INVALID, "null argument");
+  const size_t n = (size_t)nt * nr;
+  const auto sl = split_batch(nullptr, nb, 1 + (int)ctx->peers.size());
+  return run_on_all(ctx, sl, [&](twoace_ctx* c, const BatchSlice& s) {
+    return angle_single(c, mem, s.b1 - s.b0, nt, nr, L, nqt, nqr, searching_area, wavelength, spacing,
+                        X_est + 2 * (size_t)s.b0 * n, angles_true + (size_t)s.b0 * 2 * L, out + (size_t)s.b0 * ANG_WORDS);
+  });
+}
+
 extern "C" int twoace_set_timing(twoace_ctx* ctx, int on) {
   if (!ctx) return TWOACE_E_INVALID;
   ctx->timing = on != 0;

@@ -188,3 +188,148 @@ __global__ void __launch_bounds__(NT) metrics_kernel(const cd* __restrict__ Xest
 }
 
 }  // namespace twoace
+
+// ------------------------------------------------------------------------------------------------------------------
+// AoD / AoA estimation error (Numerical_Simulation/src/evaluate_plot_results/Evaluation_Recovery.m:85-146) of an
+// H-domain estimate: its angular spectrum z = vec(A_Rx' H A_Tx) on the virtual-angle dictionary of
+// generate_channel/Sparse_Channel_Formulation.m:83-103, restricted to the searching area (:120-152, AoD index outer),
+// plays the role of `recoveredSig`; the L largest entries give the estimated angles.  One CTA per instance.
+//   out[0..5] = AoD_Err_to_True, AoA_Err_to_True, AoDA_Err, AoD_Err_to_True_Quantized, AoA_Err_to_True_Quantized,
+//               AoDA_Err_Quantized   (degrees; NaN for a non-finite estimate)
+// Kept quirk: :133 `AoA_True(order_True) = AoA_True(order_True)` is a no-op, the true AoAs stay in path order.
+namespace twoace {
+
+constexpr int ANG_WORDS = 6;
+constexpr int ANG_LMAX = 32;
+
+struct AngDims {
+  int nt, nr, L, nqt, nqr;
+  int u0, u1, v0, v1;        // inclusive grid index ranges covering the searching area
+  double kph;                // 2 pi d / lambda
+  size_t ws_stride;          // doubles per CTA: 2 nv nt (W) + nv nu (|z|^2)
+};
+
+__global__ void __launch_bounds__(NT) angle_metrics_kernel(const cd* __restrict__ Xest, const double* __restrict__ ang_true,
+                                                          int nb, AngDims dm, double* __restrict__ out, double* wsbase) {
+  __shared__ double s_val[NW];
+  __shared__ int s_idx[NW];
+  __shared__ int s_top[ANG_LMAX];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = dm.nt, nr = dm.nr, L = dm.L, n = nt * nr;
+  const int nu = dm.u1 - dm.u0 + 1, nv = dm.v1 - dm.v0 + 1;
+  cd* W = (cd*)(wsbase + (size_t)blockIdx.x * dm.ws_stride);
+  double* mag = (double*)(W + (size_t)nv * nt);
+  const double PI = 3.14159265358979323846;
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    const cd* H = Xest + (size_t)b * n;            // H[kr + nr kt]
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int idx = tid; idx < nv * nt; idx += NT) {          // W = A_Rx(:, v)' H
+      const int vi = idx % nv, kt = idx / nv;
+      const double phi = dm.kph * (-1.0 + 2.0 * (double)(dm.v0 + vi) / (double)dm.nqr);
+      cd acc = cmk(0.0, 0.0);
+      for (int kr = 0; kr < nr; ++kr) {
+        double s, c;
+        sincos(phi * kr, &s, &c);
+        cfma(acc, cmk(c, s), H[kr + nr * kt]);               // conj(exp(-j phi kr))
+      }
+      W[idx] = cscale(acc, 1.0 / sqrt((double)nr));
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nv * nu; idx += NT) {          // z = W A_Tx(:, u), entry ui * nv + vi
+      const int vi = idx % nv, ui = idx / nv;
+      const double phi = dm.kph * (-1.0 + 2.0 * (double)(dm.u0 + ui) / (double)dm.nqt);
+      cd acc = cmk(0.0, 0.0);
+      for (int kt = 0; kt < nt; ++kt) {
+        double s, c;
+        sincos(phi * kt, &s, &c);
+        cfma(acc, cmk(c, -s), W[vi + nv * kt]);
+      }
+      const double m2 = cabs2(acc) / (double)nt;
+      if (!(m2 == m2) || isinf(m2)) s_bad = 1;
+      mag[idx] = m2;
+    }
+    __syncthreads();
+    if (s_bad) {
+      if (tid < ANG_WORDS) out[(size_t)b * ANG_WORDS + tid] = NAN;
+      __syncthreads();
+      continue;
+    }
+    for (int l = 0; l < L; ++l) {                            // the L largest entries, first index on ties (:86-87)
+      double bv = -1.0;
+      int bi = 0x7fffffff;
+      for (int idx = tid; idx < nv * nu; idx += NT) {
+        const double v = mag[idx];
+        if (v > bv) { bv = v; bi = idx; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < NW; ++w)
+          if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+        s_top[l] = bi;
+        mag[bi] = -2.0;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int ind[ANG_LMAX];
+      double aod_e[ANG_LMAX], aoa_e[ANG_LMAX], aod_t[ANG_LMAX], aoa_t[ANG_LMAX], aod_q[ANG_LMAX], aoa_q[ANG_LMAX];
+      for (int l = 0; l < L; ++l) ind[l] = s_top[l];
+      for (int i = 1; i < L; ++i) {                          // :88 sort ascending
+        const int key = ind[i];
+        int j = i - 1;
+        while (j >= 0 && ind[j] > key) { ind[j + 1] = ind[j]; --j; }
+        ind[j + 1] = key;
+      }
+      const double r2d = 180.0 / PI;
+      for (int l = 0; l < L; ++l) {
+        const int ui = ind[l] / nv, vi = ind[l] % nv;
+        aod_e[l] = asin(-1.0 + 2.0 * (double)(dm.u0 + ui) / (double)dm.nqt) * r2d;       // :104-113
+        aoa_e[l] = asin(-1.0 + 2.0 * (double)(dm.v0 + vi) / (double)dm.nqr) * r2d;
+        const double td = ang_true[(size_t)b * 2 * L + l], ta = ang_true[(size_t)b * 2 * L + L + l];
+        aod_t[l] = td; aoa_t[l] = ta;
+        // nearest grid point of the true virtual angle, first minimum (Sparse_Channel_Formulation.m:105-113)
+        const double sd = sin(td * PI / 180.0), sa = sin(ta * PI / 180.0);
+        int pd = 0, pa = 0;
+        double ed = INFINITY, ea = INFINITY;
+        for (int q = 0; q < dm.nqt; ++q) { const double e = fabs(dm.kph * (-1.0 + 2.0 * q / (double)dm.nqt) - dm.kph * sd); if (e < ed) { ed = e; pd = q; } }
+        for (int q = 0; q < dm.nqr; ++q) { const double e = fabs(dm.kph * (-1.0 + 2.0 * q / (double)dm.nqr) - dm.kph * sa); if (e < ea) { ea = e; pa = q; } }
+        aod_q[l] = asin(-1.0 + 2.0 * pd / (double)dm.nqt) * r2d;                         // :115-123
+        aoa_q[l] = asin(-1.0 + 2.0 * pa / (double)dm.nqr) * r2d;
+      }
+      // :132-137 stable descending sorts: true AoD (carrying the quantised pairs, NOT the true AoA), estimated AoD
+      for (int i = 1; i < L; ++i) {
+        const double kd = aod_t[i], kq = aod_q[i], ka = aoa_q[i];
+        int j = i - 1;
+        while (j >= 0 && aod_t[j] < kd) { aod_t[j + 1] = aod_t[j]; aod_q[j + 1] = aod_q[j]; aoa_q[j + 1] = aoa_q[j]; --j; }
+        aod_t[j + 1] = kd; aod_q[j + 1] = kq; aoa_q[j + 1] = ka;
+      }
+      for (int i = 1; i < L; ++i) {
+        const double kd = aod_e[i], ka = aoa_e[i];
+        int j = i - 1;
+        while (j >= 0 && aod_e[j] < kd) { aod_e[j + 1] = aod_e[j]; aoa_e[j + 1] = aoa_e[j]; --j; }
+        aod_e[j + 1] = kd; aoa_e[j + 1] = ka;
+      }
+      double e_d = 0.0, e_a = 0.0, e_dq = 0.0, e_aq = 0.0;
+      for (int l = 0; l < L; ++l) {
+        e_d += fabs(aod_e[l] - aod_t[l]); e_a += fabs(aoa_e[l] - aoa_t[l]);
+        e_dq += fabs(aod_e[l] - aod_q[l]); e_aq += fabs(aoa_e[l] - aoa_q[l]);
+      }
+      e_d /= L; e_a /= L; e_dq /= L; e_aq /= L;
+      double* o = out + (size_t)b * ANG_WORDS;
+      o[0] = e_d; o[1] = e_a;
+      o[2] = nt == 1 ? e_a : (nr == 1 ? e_d : 0.5 * (e_d + e_a));                         // :144-151
+      o[3] = e_dq; o[4] = e_aq; o[5] = 0.5 * (e_dq + e_aq);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace twoace

@@ -16,6 +16,7 @@ INFO_WORDS = 16
 STAGE_WORDS = 16
 PL_INFO_WORDS = 16
 METRIC_WORDS = 4
+ANGLE_WORDS = 6
 
 # every symbol include/twoace.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -25,7 +26,7 @@ EXPORTS = [
     "twoace_spectral_init_batch", "twoace_set_timing", "twoace_timing_collect", "twoace_fp64_peak",
     "twoace_set_option", "twoace_fast_launch_count", "twoace_tensor_launch_count", "twoace_set_trace", "twoace_pl_default_opts", "twoace_phaselift_batch",
     "twoace_metrics_batch", "twoace_synth_default_params", "twoace_synth_batch",
-    "twoace_create_multi", "twoace_device_count",
+    "twoace_create_multi", "twoace_device_count", "twoace_angle_metrics_batch",
 ]
 
 
@@ -155,6 +156,9 @@ def load() -> C.CDLL:
     lib.twoace_phaselift_batch.restype = C.c_int
     lib.twoace_metrics_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]
     lib.twoace_metrics_batch.restype = C.c_int
+    lib.twoace_angle_metrics_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                               C.c_double, C.c_double, dp, dp, dp]
+    lib.twoace_angle_metrics_batch.restype = C.c_int
     lib.twoace_synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int, C.c_int]
     lib.twoace_synth_default_params.restype = None
     lib.twoace_synth_batch.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SynthParams), i32p, dp, i32p, i32p, vp, i32p, i32p,
@@ -292,6 +296,10 @@ class Context:
     def metrics_batch_raw(self, mem, nb, tx, rx, X_est, X_true, phase_bit, out):
         self.check(self.lib.twoace_metrics_batch(self.h, mem, nb, tx, rx, _ptr(X_est), _ptr(X_true), int(phase_bit),
                                                  _ptr(out)))
+
+    def angle_metrics_batch_raw(self, mem, nb, nt, nr, L, nqt, nqr, searching_area, wavelength, spacing, X_est, angles, out):
+        self.check(self.lib.twoace_angle_metrics_batch(self.h, mem, nb, nt, nr, L, nqt, nqr, float(searching_area),
+                                                       float(wavelength), float(spacing), _ptr(X_est), _ptr(angles), _ptr(out)))
 
     def synth_batch_raw(self, mem, nb, sp, m, snr_db, row_lo, row_hi, trial_id, cb_rows, train_idx, B, vecH, angles=None):
         self.check(self.lib.twoace_synth_batch(self.h, mem, nb, C.byref(sp), _ptr(m), _ptr(snr_db), _ptr(row_lo),

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 METRICS = ("count", "sum_mse", "n_rank_one", "n_rollback", "sum_quality", "sum_iters", "sum_gain_ana", "sum_gain_dig",
-           "sum_proj_err")
+           "sum_proj_err", "sum_aoda_err")
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -22,7 +22,7 @@ def shard_range(total: int, rank: int, world: int):
     return lo, hi
 
 
-def local_stats(cell_ids, n_cells: int, mse, info, metrics=None) -> np.ndarray:
+def local_stats(cell_ids, n_cells: int, mse, info, metrics=None, angle_metrics=None) -> np.ndarray:
     """Accumulate per-cell sums for the instances of this rank.
     cell_ids: int [nb] (e.g. index into the SNR x M grid); mse: [nb]; info: [nb,16] (twoace.h words);
     metrics: optional [nb,4] from twoace_metrics_batch (MSE_H, gain_ana, gain_dig, proj_error), summed over the
@@ -41,12 +41,16 @@ def local_stats(cell_ids, n_cells: int, mse, info, metrics=None) -> np.ndarray:
         metrics = np.asarray(metrics, dtype=np.float64)
         for k in range(3):
             np.add.at(s[:, 6 + k], cell_ids[ok], np.nan_to_num(metrics[ok, 1 + k]))
+    if angle_metrics is not None:      # AoDA_Err of twoace_angle_metrics_batch (Evaluation_Recovery.m:144-151), degrees
+        a = np.asarray(angle_metrics, dtype=np.float64)[:, 2]
+        np.add.at(s[:, 9], cell_ids[ok], np.nan_to_num(a[ok]))
     return s
 
 
-def local_stats_device(cell_ids, n_cells: int, info, metrics):
+def local_stats_device(cell_ids, n_cells: int, info, metrics, angle_metrics=None):
     """local_stats on the device with torch ops (no host round trip): cell_ids int64 [nb], info [nb,16],
-    metrics [nb,4] CUDA tensors -> [n_cells, len(METRICS)] float64 on the same device and stream."""
+    metrics [nb,4], angle_metrics [nb,6] or None: CUDA tensors -> [n_cells, len(METRICS)] float64 on the same device and
+    stream."""
     import torch
     mse = metrics[:, 0]
     ok = torch.isfinite(mse)
@@ -54,6 +58,7 @@ def local_stats_device(cell_ids, n_cells: int, info, metrics):
     z = torch.zeros_like(mse)
     cols = [okf, torch.where(ok, mse, z), info[:, 2], info[:, 3], torch.nan_to_num(info[:, 0]), info[:, 15]]
     cols += [torch.where(ok, torch.nan_to_num(metrics[:, 1 + k]), z) for k in range(3)]
+    cols.append(torch.where(ok, torch.nan_to_num(angle_metrics[:, 2]), z) if angle_metrics is not None else z)
     payload = torch.stack(cols, dim=1)
     s = torch.zeros((n_cells, len(METRICS)), dtype=torch.float64, device=mse.device)
     return s.index_add_(0, cell_ids, payload)

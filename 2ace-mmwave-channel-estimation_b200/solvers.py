@@ -227,6 +227,21 @@ def evaluation_batch(X_est, X_true, tx: int, rx: int, phase_bit: int = 2, ctx: _
     return out
 
 
+def angle_evaluation_batch(X_est, angles_true, tx: int, rx: int, nqt: int | None = None, nqr: int | None = None,
+                           searching_area: float = 95.0, wavelength: float = 3e8 / 60.48e9, spacing: float = 3.055e-3,
+                           ctx: _lib.Context | None = None):
+    """Evaluation_Recovery.m:85-146 per instance -> [nb, 6] = (AoD_Err_to_True, AoA_Err_to_True, AoDA_Err and the same
+    three against the quantised true angles), degrees.  angles_true: [nb, 2L] (AoD then AoA)."""
+    ctx = ctx or _lib.default_context()
+    Xe = np.ascontiguousarray(np.asarray(X_est, np.complex128))
+    ang = np.ascontiguousarray(np.asarray(angles_true, np.float64))
+    nb, L = Xe.shape[0], ang.shape[1] // 2
+    out = np.empty((nb, _lib.ANGLE_WORDS), np.float64)
+    ctx.angle_metrics_batch_raw(_lib.MEM_HOST, nb, int(tx), int(rx), L, nqt or 4 * tx, nqr or 4 * rx, searching_area,
+                                wavelength, spacing, Xe, ang, out)
+    return out
+
+
 # ----------------------------------------------------------------------------- MATLAB-signature calls
 def synth_batch(m, snr_db, row_lo, row_hi, trial_id, sp: "_lib.SynthParams | None" = None,
                 ctx: _lib.Context | None = None):

@@ -320,7 +320,10 @@ def ours_arm(args, wl, rank, local_rank, world):
         tr_h = np.empty(int((mtr * T).sum()), np.int32)
         B_d = torch.empty(int(m.sum()), dtype=torch.float64, device=dev)
         Xt_d = torch.empty(nb * N * 2, dtype=torch.float64, device=dev)
-        ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows_h, tr_h, B_d.data_ptr(), Xt_d.data_ptr())
+        ang_d = torch.empty(nb * 2 * sp.L, dtype=torch.float64, device=dev)
+        angm_d = torch.empty(nb * tw.lib.ANGLE_WORDS, dtype=torch.float64, device=dev)
+        ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows_h, tr_h, B_d.data_ptr(), Xt_d.data_ptr(),
+                            ang_d.data_ptr())
         B_h = B_d.cpu().numpy()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # L2 flush between steps (126 MB L2)
     sum_m = int(m.sum())
@@ -349,8 +352,13 @@ def ours_arm(args, wl, rank, local_rank, world):
         """Evaluation metrics on the device (Evaluation_H.m:81-115), per-cell sums, and the ONE collective of the path:
         the all-reduce of the statistics tensor (NCCL over NVLink when world > 1) -- all inside the timed step."""
         ctx.metrics_batch_raw(tw.lib.MEM_DEVICE, nb, TX, RX, X_d.data_ptr(), Xt_d.data_ptr(), 2, met_d.data_ptr())
+        angm = None
+        if not dense:      # AoD / AoA error (Evaluation_Recovery.m:85-146): the true angles come from the synthesis
+            ctx.angle_metrics_batch_raw(tw.lib.MEM_DEVICE, nb, TX, RX, sp.L, 4 * TX, 4 * RX, sp.searching_area,
+                                        sp.wavelength, sp.spacing, X_d.data_ptr(), ang_d.data_ptr(), angm_d.data_ptr())
+            angm = angm_d.view(nb, tw.lib.ANGLE_WORDS)
         with torch.cuda.stream(stream):
-            st = par.local_stats_device(cells_d, n_cells, info_d.view(nb, 16), met_d.view(nb, W))
+            st = par.local_stats_device(cells_d, n_cells, info_d.view(nb, 16), met_d.view(nb, W), angm)
             if world > 1:
                 dist.all_reduce(st)
         stats_box[0] = st
@@ -455,7 +463,8 @@ def ours_arm(args, wl, rank, local_rank, world):
         rows2, tr2 = np.empty_like(rows_h), np.empty_like(tr_h)
 
         def step_synth():
-            ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows2, tr2, B_d.data_ptr(), Xt_d.data_ptr())
+            ctx.synth_batch_raw(tw.lib.MEM_DEVICE, nb, sp, m, snr, lo, hi, tid, rows2, tr2, B_d.data_ptr(), Xt_d.data_ptr(),
+                                ang_d.data_ptr())
             ctx.solve_batch_codebook_raw(variant, tw.lib.MEM_DEVICE, nb, TX, RX, m, rows2, row_scale, B_d.data_ptr(), tr2, p,
                                          X_d.data_ptr(), Y_d.data_ptr(), q_d.data_ptr(), info_d.data_ptr(), None)
             evaluate_and_reduce()
@@ -504,7 +513,8 @@ def ours_arm(args, wl, rank, local_rank, world):
                            "input_mode": "dense complex128 A per instance, instances built on the host" if dense else
                                          "codebook rows (codebook registered once); instances built on the device by "
                                          "twoace_synth_batch (Philox4x32-10 keyed by the global trial id)",
-                           "timed_step": "solve + evaluation metrics + per-cell statistics + all-reduce of the statistics",
+                           "timed_step": "solve + evaluation metrics (Evaluation_H, AoD/AoA error) + per-cell statistics + all-reduce of "
+                                         "the statistics",
                            "cache": f"inputs larger than L2 ({A_h.nbytes / 1e6:.0f} MB dense A per step)" if dense else
                                     "L2 flushed between steps (256 MB device memset on the solver's stream)",
                            "mean_iters_per_solve": float(info[:, 15].mean()),
@@ -514,7 +524,8 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "clocks": clocks, "nmse_delta_db": nmse_delta,
                 "nmse_db_per_cell": [None if not np.isfinite(v) else float(v) for v in par.nmse_db_per_cell(stats)],
                 "metrics_mean": {k: float(stats[:, 6 + j].sum() / max(stats[:, 0].sum(), 1.0))
-                                 for j, k in enumerate(("gain_ana", "gain_dig", "proj_error"))},
+                                 for j, k in enumerate(("gain_ana", "gain_dig", "proj_error", "aoda_err_deg"))},
+                "aoda_err_deg_per_cell": [float(v) for v in (stats[:, 9] / np.maximum(stats[:, 0], 1.0))],
                 "e2e_vs_device_max_abs_diff": e2e_match}
         print(json.dumps(line), flush=True)
 

@@ -202,6 +202,18 @@ int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_
 int twoace_metrics_batch(twoace_ctx* ctx, int mem, int nb, int tx, int rx, const double* X_est,
                          const double* X_true, int phase_bit, double* out);
 
+/* AoD / AoA estimation error per instance (Numerical_Simulation/src/evaluate_plot_results/Evaluation_Recovery.m:85-146)
+ * of an H-domain estimate X_est[b] (vec of the nr x nt channel): its angular spectrum z = vec(A_Rx' H A_Tx) on the
+ * nqt x nqr virtual-angle dictionary of generate_channel/Sparse_Channel_Formulation.m:83-103, restricted to the
+ * searching area (degrees, :120-152), stands in for `recoveredSig`; the L largest entries give the estimated angles.
+ * angles_true: nb x 2L (AoD then AoA of the L paths, degrees -- the `angles` output of twoace_synth_batch).
+ * out[b*6 + k]: 0 AoD_Err_to_True, 1 AoA_Err_to_True, 2 AoDA_Err, 3..5 the same against the quantised true angles
+ * (degrees; NaN for a non-finite estimate).  Reference grid: nqt = 4 nt, nqr = 4 nr (Vs_M_par.m:80-81). */
+#define TWOACE_ANGLE_WORDS 6
+int twoace_angle_metrics_batch(twoace_ctx* ctx, int mem, int nb, int nt, int nr, int L, int nqt, int nqr,
+                               double searching_area, double wavelength, double spacing, const double* X_est,
+                               const double* angles_true, double* out);
+
 /* ---- On-device instance synthesis -----------------------------------------------------
  * Builds nb independent (trial, M, SNR) instances of the numerical-simulation workload on the GPU, so that the
  * 100k / 1M-trial configurations need no per-instance host->device input traffic:

@@ -103,3 +103,31 @@ def test_multi_gpu_context_equals_single_gpu(gpu_ctx):
     m2 = sv.evaluation_batch(r2.X, a["vecH"], 16, 16, ctx=mctx)
     assert np.array_equal(np.asarray(m1), np.asarray(m2), equal_nan=True)
     mctx.close()
+
+
+@pytest.mark.parametrize("tx,rx,L", [(16, 16, 3), (8, 4, 2), (32, 32, 5)])
+def test_angle_error_metric_parity(gpu_ctx, tx, rx, L):
+    """AoD / AoA error (Evaluation_Recovery.m:85-146) on the device against oracle/metrics.py: exact estimates, noisy
+    estimates, a NaN estimate.  Angles are grid values (asin of grid points), so agreement is to rounding."""
+    from oracle import metrics as om
+    from twoace_b200 import solvers as sv
+    rng = np.random.default_rng(7)
+    n, nb = tx * rx, 9
+    X, ang = [], []
+    for b in range(nb):
+        aod, aoa = rng.uniform(-47.5, 47.5, L), rng.uniform(-47.5, 47.5, L)
+        g = rng.standard_normal(L) + 1j * rng.standard_normal(L)
+        kph = 2 * np.pi * 3.055e-3 / (3e8 / 60.48e9)
+        at = np.exp(-1j * kph * np.sin(np.deg2rad(aod))[None, :] * np.arange(tx)[:, None])
+        ar = np.exp(-1j * kph * np.sin(np.deg2rad(aoa))[None, :] * np.arange(rx)[:, None])
+        H = (ar * g[None, :]) @ at.conj().T
+        x = H.reshape(-1, order="F")
+        if b % 3 == 1:
+            x = x + 0.3 * np.linalg.norm(x) / np.sqrt(n) * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        if b == 5:
+            x = np.full(n, np.nan + 0j)
+        X.append(x); ang.append(np.concatenate([aod, aoa]))
+    out = sv.angle_evaluation_batch(np.array(X), np.array(ang), tx, rx, ctx=gpu_ctx)
+    for b in range(nb):
+        want = om.evaluation_angles(X[b], ang[b][:L], ang[b][L:], tx, rx)
+        assert np.allclose(out[b], want, rtol=0, atol=1e-9, equal_nan=True), (b, out[b], want)

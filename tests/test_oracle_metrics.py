@@ -45,3 +45,28 @@ def test_nan_estimate_gives_nan():
     x = vecH.copy()
     x[3] = np.nan
     assert all(np.isnan(v) for v in om.evaluation_h(x, vecH, 16, 16))
+
+
+def test_angle_error_oracle_properties():
+    """Evaluation_Recovery.m:85-146 restated on the angular spectrum of an H-domain estimate."""
+    from oracle import metrics as om
+    Nt = Nr = 16
+    kph, aod_v, aoa_v, (u0, u1), (v0, v1) = om.angle_grid(Nt, Nr, 64, 64, 95.0)
+    # the searching area maps to a centred index range of the 64-point grid (sin(47.5 deg) = 0.737)
+    assert (u0, u1) == (v0, v1) and u0 + u1 == 64 and 44 <= u1 - u0 + 1 <= 50
+    # a single on-grid path is found exactly: all six errors vanish
+    u, v = 40, 22
+    aod = np.rad2deg(np.arcsin(aod_v[u] / kph))
+    aoa = np.rad2deg(np.arcsin(aoa_v[v] / kph))
+    at = np.exp(-1j * aod_v[u] * np.arange(Nt)) / 4
+    ar = np.exp(-1j * aoa_v[v] * np.arange(Nr)) / 4
+    H = np.outer(ar, at.conj()) * (0.3 - 0.8j)
+    errs = om.evaluation_angles(H.reshape(-1, order="F"), [aod], [aoa], Nt, Nr)
+    assert np.allclose(errs, 0.0, atol=1e-9)
+    # off-grid path: the error is bounded by the grid spacing in degrees near that angle
+    errs = om.evaluation_angles(H.reshape(-1, order="F"), [aod + 0.4], [aoa - 0.3], Nt, Nr)
+    assert abs(errs[0] - 0.4) < 1e-9 and abs(errs[1] - 0.3) < 1e-9 and errs[3] < 1e-9
+    # a global phase / scale of the estimate changes nothing; NaN estimates give NaN
+    e1 = om.evaluation_angles(H.reshape(-1, order="F") * (2.0 * np.exp(0.7j)), [aod], [aoa], Nt, Nr)
+    assert np.allclose(e1, 0.0, atol=1e-9)
+    assert all(np.isnan(om.evaluation_angles(np.full(256, np.nan + 0j), [aod], [aoa], Nt, Nr)))

@@ -34,7 +34,8 @@ def _fake_results(lo, hi):
     mse[t % 11 == 5] = np.nan      # failed solves are skipped, not summed
     met = np.stack([mse, 2.0 + rng_vals, 2.5 + rng_vals, 0.9 * rng_vals], axis=1)   # twoace_metrics_batch layout
     met[np.isnan(mse)] = np.nan
-    return cells, mse, info, met
+    ang = np.stack([3.0 + rng_vals] * 6, axis=1)                                    # twoace_angle_metrics_batch layout
+    return cells, mse, info, met, ang
 
 
 def _worker(rank, world, port, total, q):
@@ -42,8 +43,8 @@ def _worker(rank, world, port, total, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = par.shard_range(total, rank, world)
-    cells, mse, info, met = _fake_results(lo, hi)
-    s = par.all_reduce_stats(par.local_stats(cells, 4, mse, info, met))
+    cells, mse, info, met, ang = _fake_results(lo, hi)
+    s = par.all_reduce_stats(par.local_stats(cells, 4, mse, info, met, ang))
     q.put((rank, s))
     dist.barrier()
     dist.destroy_process_group()
@@ -63,11 +64,12 @@ def test_two_rank_stats_equal_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    cells, mse, info, met = _fake_results(0, total)
-    ref = par.local_stats(cells, 4, mse, info, met)
+    cells, mse, info, met, ang = _fake_results(0, total)
+    ref = par.local_stats(cells, 4, mse, info, met, ang)
     assert ref.shape == (4, len(par.METRICS)) and np.all(ref[:, 6:] > 0)      # the gains / projection error ride along
     ok = np.isfinite(mse)
     assert abs(ref[:, 7].sum() - met[ok, 2].sum()) < 1e-9
+    assert abs(ref[:, 9].sum() - ang[ok, 2].sum()) < 1e-9                      # the AoD/AoA error word of SURVEY 8e
     for r in range(world):
         np.testing.assert_allclose(got[r], ref, rtol=1e-13)
     db = par.nmse_db_per_cell(ref)

@@ -10,8 +10,8 @@ batch in codebook mode (A is never materialised per instance).
 
 Not reproduced: MATLAB's RNG stream (randperm / randsample).  The row subsets and train
 splits are drawn from a NumPy Generator seeded with the same integer seeds, or passed explicitly.
-The `phaselift` entry point (MyPhaseLift through Recover_Channel.m:33-36) is mirrored as well; `directional`
-runs PLOMP / PLGAMP and is outside this build.
+The `phaselift` entry point (MyPhaseLift through Recover_Channel.m:33-36) and `directional` (PLOMP / PLGAMP: stage I on
+the GPU, the SVD reduction and the sparse step II on the host, see twostage.py) are mirrored as well.
 """
 from __future__ import annotations
 
@@ -155,3 +155,70 @@ def channel_recovery_ADMM_v2_simulation_phaselift(tx_ant_num, rx_ant_num, cb_amp
     H_out[np.isnan(H_out)] = 0
     amp, ang = np.abs(H_out), np.angle(H_out)
     return (amp, ang, dict(M=Ms, rows=rows, sig=sig, info=info)) if details else (amp, ang)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+DIRECTIONAL_SPACING = 2.9e-3                         # …_directional.m:36 (ULA.d; the other entry points use 3.055e-3)
+DIRECTIONAL_L = 3                                    # …_directional.m:52
+
+
+def sparse_dictionary(Nt: int, Nr: int, NQt: int, NQr: int, spacing: float = DIRECTIONAL_SPACING,
+                      wavelength: float = 3e8 / 60.48e9) -> np.ndarray:
+    """AD of Sparse_Channel_Formulation.m:83-152 for Searching_Area = 180 (…_directional.m:46): both ends of the area
+    map to the first / last grid point, so the dictionary holds every (AoD u, AoA v) pair, u outer:
+    AD(:, u * NQr + v) = kron(conj(A_Tx(:, u)), A_Rx(:, v)).  It does not depend on the drawn channel H
+    (…_directional.m:148-149 generate one only to obtain this matrix)."""
+    kph = 2 * np.pi * spacing / wavelength
+    aod_v = kph * np.linspace(-1, 1, NQt + 1)[:-1]
+    aoa_v = kph * np.linspace(-1, 1, NQr + 1)[:-1]
+    A_Tx = np.exp(-1j * aod_v[None, :] * np.arange(Nt)[:, None]) / np.sqrt(Nt)
+    A_Rx = np.exp(-1j * aoa_v[None, :] * np.arange(Nr)[:, None]) / np.sqrt(Nr)
+    # kron(conj(a_t), a_r)[kt * Nr + kr] = conj(a_t[kt]) a_r[kr]
+    AD = (A_Tx.conj()[:, None, :, None] * A_Rx[None, :, None, :]).reshape(Nt * Nr, NQt * NQr)
+    return AD
+
+
+def directional_indexing(M_cur: int) -> np.ndarray:
+    """0-based beam indices along one side of the 32 x 32 directional codebook (…_directional.m:137-141)."""
+    k = M_cur if M_cur <= 32 else 32
+    return (matlab_round(np.linspace(1, 32, k)) - 1).astype(np.int64)
+
+
+def channel_recovery_ADMM_v2_simulation_directional(tx_ant_num, rx_ant_num, cb_amp, cb_angle, rss_final, seed_id=1, *,
+                                                    opts=None, ctx=None, details=False):
+    """directional: PLOMP and PLGAMP (two-stage recovery) on a sub-grid of the 32 x 32 directional codebook
+    (main/channel_recovery_ADMM_v2_simulation_directional.m:9-175 -> Recover_Channel.m:37-43 ->
+    My_TwoStage_Recovery.m).  cb_amp / cb_angle: 32 x 32 x (tx*rx); rss_final: 32 x 32 dBm.  Output [8, 2, n]:
+    method 0 = PLOMP, 1 = PLGAMP.  Stage I (PhaseLift on the mCS x mCS programme) runs on the GPU; the SVD reduction and
+    the sparse step II are host code, as they are CPU code in the reference (see twostage.py for what step II is)."""
+    from . import twostage as _ts
+    tx, rx = int(tx_ant_num), int(rx_ant_num)
+    n = tx * rx
+    cb = np.asarray(cb_amp, dtype=np.float64) * np.exp(1j * np.asarray(cb_angle, dtype=np.float64))        # :128
+    if cb.ndim != 3 or cb.shape[:2] != (32, 32) or cb.shape[2] != n:
+        raise ValueError(f"directional codebook must be 32 x 32 x {n}, got {cb.shape}")
+    rss = np.asarray(rss_final, dtype=np.float64)
+    if rss.shape != (32, 32):
+        raise ValueError("rss_final must be 32 x 32 for the directional codebook")
+    if not any(a in (8, 16, 17, 32, 36) for a in (tx, rx)):
+        raise ValueError("Number of antenna on Tx and Rx must be 4/8/16/32!")
+    a_t, a_r = (tx - 1, rx - 1) if 17 in (tx, rx) else (tx, rx)
+    Mt = matlab_round(np.linspace(2, np.sqrt(4 * a_t * a_r), 8)).astype(np.int64)                            # :107-125
+    AD = sparse_dictionary(tx, rx, 4 * tx, 4 * rx)                                                          # :40-41,149
+    H_out = np.zeros((len(Mt), 2, n), dtype=np.complex128)
+    info = []
+    for i, M_cur in enumerate(Mt):
+        idx = directional_indexing(int(M_cur))
+        k = len(idx)
+        cb_train = cb[np.ix_(idx, idx)]                                                                     # :142
+        beams = cb_train.reshape(k * k, n, order="F")                                                       # :143
+        rss_train = rss[np.ix_(idx, idx)].reshape(k * k, order="F")                                         # :144-145
+        measurements = rss_dbm_to_amplitude(rss_train)                                                      # :146
+        y = (measurements / 2e5) ** 2 * 1e10                                                                # Recover_Channel.m:40
+        plomp, plgamp, d = _ts.my_two_stage_recovery(y, beams @ AD, DIRECTIONAL_L, opts=opts, ctx=ctx, details=True)
+        H_out[i, 0, :] = AD @ plomp / np.sqrt(1e10) * 2e5 / RSS_FCT                                         # :41, :160
+        H_out[i, 1, :] = AD @ plgamp / np.sqrt(1e10) * 2e5 / RSS_FCT
+        info.append(dict(M=int(M_cur), probes=k * k, mCS=d["mCS"], pl_info=d["info"]))
+    H_out[np.isnan(H_out)] = 0                                                                              # :166
+    amp, ang = np.abs(H_out), np.angle(H_out)
+    return (amp, ang, dict(M=Mt, stages=info)) if details else (amp, ang)

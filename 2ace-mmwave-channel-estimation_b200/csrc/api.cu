@@ -1417,9 +1417,9 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
 
   const size_t smem = pl_smem_bytes(n, maxm);
   if (smem > 227 * 1024) FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift: m = %d needs %zu bytes of shared memory", maxm, smem);
-  CK(cudaFuncSetAttribute(phaselift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(pl_kernel_set_smem(smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, phaselift_kernel, NT, smem));
+  CK(pl_kernel_occupancy(&per_sm, smem));
   if (per_sm < 1) FAIL(TWOACE_E_CUDA, "PhaseLift kernel does not fit on an SM");
   // longest solves first is not knowable up front; instances are handed out dynamically through a counter
   const int grid = std::min(nb, per_sm * ctx->num_sms);
@@ -1459,8 +1459,7 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
   }
-  phaselift_kernel<<<grid, NT, smem, ctx->stream>>>(dt, nb, n, maxm, po, (cd*)(base + o_ws), ws_stride, d_cnt);
-  CK(cudaGetLastError());
+  CK(pl_kernel_launch(grid, smem, ctx->stream, dt, nb, n, maxm, po, (cd*)(base + o_ws), ws_stride, d_cnt));
   ctx->launches++;
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));

@@ -648,6 +648,15 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
   __syncthreads();
 }
 
+// The kernel lives in its own translation unit (pl_kernel.cu): compiled together with the ADMM kernels in one module
+// the inliner outlined parts of the prox (stack 720 -> 1232 bytes per thread) and config 3 lost 20 % (r02 measurement).
+// api.cu reaches it through these three host functions.
+cudaError_t pl_kernel_set_smem(size_t smem);
+cudaError_t pl_kernel_occupancy(int* per_sm, size_t smem);
+cudaError_t pl_kernel_launch(int grid, size_t smem, cudaStream_t stream, const PlTask* tasks, int ntasks, int n, int maxm,
+                             PlOpts o, cd* wsbase, size_t ws_stride, int* counter);
+
+#ifdef TWOACE_PL_KERNEL_TU
 __global__ void __launch_bounds__(NT, 2) phaselift_kernel(const PlTask* tasks, int ntasks, int n, int maxm, PlOpts o,
                                                        cd* wsbase, size_t ws_stride, int* counter) {
   extern __shared__ __align__(16) unsigned char pl_smem_raw[];
@@ -661,5 +670,18 @@ __global__ void __launch_bounds__(NT, 2) phaselift_kernel(const PlTask* tasks, i
     run_phaselift(tasks[t], n, maxm, o, wsbase + (size_t)blockIdx.x * ws_stride, pl_smem_raw);
   }
 }
+
+cudaError_t pl_kernel_set_smem(size_t smem) {
+  return cudaFuncSetAttribute(phaselift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+cudaError_t pl_kernel_occupancy(int* per_sm, size_t smem) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, phaselift_kernel, NT, smem);
+}
+cudaError_t pl_kernel_launch(int grid, size_t smem, cudaStream_t stream, const PlTask* tasks, int ntasks, int n, int maxm,
+                             PlOpts o, cd* wsbase, size_t ws_stride, int* counter) {
+  phaselift_kernel<<<grid, NT, smem, stream>>>(tasks, ntasks, n, maxm, o, wsbase, ws_stride, counter);
+  return cudaGetLastError();
+}
+#endif
 
 }  // namespace twoace

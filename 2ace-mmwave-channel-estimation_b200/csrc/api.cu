@@ -49,6 +49,7 @@ struct twoace_ctx {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
   std::vector<std::string> stage_labels;   // one per stage_events entry (TWOACE_TRACE_LAUNCHES=1 prints them)
+  std::vector<std::pair<void*, size_t>> stage_cache;   // free device buffers of the host-pointer staging (pointer, capacity)
   std::vector<twoace_ctx*> peers;          // twoace_create_multi: the contexts of the other GPUs (this one is device 0 of the set)
 };
 
@@ -139,6 +140,7 @@ extern "C" void twoace_destroy(twoace_ctx* ctx) {
   if (ctx->taskbuf.p) cudaFree(ctx->taskbuf.p);
   if (ctx->cb_rm) cudaFree(ctx->cb_rm);
   if (ctx->cb_codes) cudaFree(ctx->cb_codes);
+  for (auto& pr : ctx->stage_cache) cudaFree(pr.first);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -958,17 +960,50 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   return 0;
 }
 
-// Host-pointer staging helper: device mirrors of inputs/outputs for one call.
+// Host-pointer staging helper: device mirrors of inputs/outputs for one call.  The buffers come from a small per-context
+// cache and go back to it when the call ends (cudaMalloc / cudaFree per call cost up to several hundred ms of host time
+// now and then on the e2e path; every user of a staged buffer is ordered on the context's stream, so reuse is safe).
 struct Staging {
-  std::vector<void*> owned;
-  ~Staging() { for (void* p : owned) cudaFree(p); }
+  twoace_ctx* ctx = nullptr;
+  std::vector<std::pair<void*, size_t>> owned;
+  ~Staging() {
+    for (auto& pr : owned) {
+      if (ctx) ctx->stage_cache.push_back(pr);
+      else cudaFree(pr.first);
+    }
+  }
 };
+
+static void* stage_alloc(twoace_ctx* ctx, Staging& st, size_t bytes) {
+  st.ctx = ctx;
+  const size_t want = (bytes + 262143) / 262144 * 262144;
+  int best = -1;
+  for (int i = 0; i < (int)ctx->stage_cache.size(); ++i) {
+    const size_t cap = ctx->stage_cache[i].second;
+    if (cap >= want && cap <= 2 * want + (1u << 20) && (best < 0 || cap < ctx->stage_cache[best].second)) best = i;
+  }
+  if (best >= 0) {
+    auto pr = ctx->stage_cache[best];
+    ctx->stage_cache.erase(ctx->stage_cache.begin() + best);
+    st.owned.push_back(pr);
+    return pr.first;
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    // release the cache and retry once
+    for (auto& pr : ctx->stage_cache) cudaFree(pr.first);
+    ctx->stage_cache.clear();
+    if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  }
+  st.owned.emplace_back(p, want);
+  return p;
+}
 
 static int dev_in(twoace_ctx* ctx, Staging& st, int mem, const void* src, size_t bytes, const void** dst) {
   if (mem == TWOACE_MEM_DEVICE || bytes == 0) { *dst = src; return 0; }
-  void* p = nullptr;
-  if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for input staging failed", bytes); }
-  st.owned.push_back(p);
+  void* p = stage_alloc(ctx, st, bytes);
+  if (!p) FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for input staging failed", bytes);
   CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   *dst = p;
   return 0;
@@ -976,9 +1011,8 @@ static int dev_in(twoace_ctx* ctx, Staging& st, int mem, const void* src, size_t
 static int dev_out(twoace_ctx* ctx, Staging& st, int mem, void* host, size_t bytes, void** dst) {
   if (host == nullptr) { *dst = nullptr; return 0; }
   if (mem == TWOACE_MEM_DEVICE) { *dst = host; return 0; }
-  void* p = nullptr;
-  if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for output staging failed", bytes); }
-  st.owned.push_back(p);
+  void* p = stage_alloc(ctx, st, bytes);
+  if (!p) FAIL(TWOACE_E_NOMEM, "cudaMalloc(%zu) for output staging failed", bytes);
   *dst = p;
   return 0;
 }

@@ -49,6 +49,12 @@ struct twoace_ctx {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
   std::vector<std::string> stage_labels;   // one per stage_events entry (TWOACE_TRACE_LAUNCHES=1 prints them)
+  cudaStream_t side_stream = nullptr;      // tiny general-kernel groups of a stage run here, beside the cluster kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  DevBuf ws_side;                          // workspace of the side stream
+  bool in_side = false;
+  int opt_overlap = 1;                     // 1: overlap the general-kernel group of a stage with its cluster-kernel groups
+  std::vector<char> stage_side;            // per stage_events entry: 1 = ran on the side stream (not summed)
   std::vector<std::pair<void*, size_t>> stage_cache;   // free device buffers of the host-pointer staging (pointer, capacity)
   std::vector<twoace_ctx*> peers;          // twoace_create_multi: the contexts of the other GPUs (this one is device 0 of the set)
 };
@@ -122,6 +128,12 @@ extern "C" int twoace_create(int device, twoace_ctx** out) {
     delete ctx;
     return TWOACE_E_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->side_stream = nullptr;     // overlap disabled; everything runs on the main stream
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   ctx->num_sms = prop.multiProcessorCount;
@@ -141,6 +153,10 @@ extern "C" void twoace_destroy(twoace_ctx* ctx) {
   if (ctx->cb_rm) cudaFree(ctx->cb_rm);
   if (ctx->cb_codes) cudaFree(ctx->cb_codes);
   for (auto& pr : ctx->stage_cache) cudaFree(pr.first);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ws_side.p) cudaFree(ctx->ws_side.p);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -436,8 +452,11 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
     CK(cudaEventRecord(e1, ctx->stream));
     ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
-    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d", tasks.size(), grid, dm.maxm, dm.maxr);
+    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d%s", tasks.size(), grid, dm.maxm, dm.maxr,
+             ctx->in_side ? " (side stream, overlaps the launches below)" : "");
     ctx->stage_labels.emplace_back(lb);
+    ctx->stage_side.resize(ctx->stage_events.size(), 0);
+    ctx->stage_side.back() = ctx->in_side ? 1 : 0;
   }
   ctx->launches++;
   return 0;
@@ -521,6 +540,24 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     else if (f2) grp[2].push_back(t);
     else gen.push_back(t);
   }
+  // The general-kernel group of a mixed launch (tiny problems such as M = 4: a few dozen latency-bound CTAs) runs on the
+  // side stream with its own workspace, beside the cluster-kernel groups, which leave SMs free (132 of 148 for CS = 4).
+  bool gen_forked = false;
+  if (ctx->opt_overlap && ctx->side_stream && !gen.empty() && gen.size() < tasks.size()) {
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    std::swap(ctx->stream, ctx->side_stream);
+    std::swap(ctx->ws, ctx->ws_side);
+    ctx->in_side = true;
+    int rc = launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
+    cudaError_t e = rc ? cudaSuccess : cudaEventRecord(ctx->ev_join, ctx->stream);
+    ctx->in_side = false;
+    std::swap(ctx->ws, ctx->ws_side);
+    std::swap(ctx->stream, ctx->side_stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) FAIL(TWOACE_E_CUDA, "cudaEventRecord on the side stream failed: %s", cudaGetErrorString(e));
+    gen_forked = true;
+  }
   for (int g = 0; g < 5; ++g) {
     std::vector<StageTask>& ft = grp[g];
     if (ft.empty()) continue;
@@ -574,6 +611,10 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     rc = launch_big1(ctx, dt, (int)big1.size(), prm, fd, &launched);
     if (rc) return rc;
     if (!launched) FAIL(TWOACE_E_CUDA, "r = 1 large-m kernel launch configuration rejected (maxm %d)", fd.maxm);
+  }
+  if (gen_forked) {      // join: later launches on the main stream see the side stream's results
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return 0;
   }
   return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
 }
@@ -1746,8 +1787,9 @@ extern "C" int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t*
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
     if (trace) fprintf(stderr, "[twoace] %9.3f ms  %s\n", ms, li < ctx->stage_labels.size() ? ctx->stage_labels[li].c_str() : "stage kernel");
+    const bool side = li < ctx->stage_side.size() && ctx->stage_side[li];
     ++li;
-    tot += ms;
+    if (!side) tot += ms;          // side-stream launches overlap main-stream ones: not part of the serial sum
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
@@ -1755,6 +1797,7 @@ extern "C" int twoace_timing_collect(twoace_ctx* ctx, double* stage_ms, int64_t*
   if (stage_launches) *stage_launches = (int64_t)ctx->stage_events.size();
   ctx->stage_events.clear();
   ctx->stage_labels.clear();
+  ctx->stage_side.clear();
   return TWOACE_OK;
 }
 
@@ -1811,6 +1854,7 @@ extern "C" int twoace_set_option(twoace_ctx* ctx, const char* key, int value) {
   else if (k == "tensor") ctx->opt_tensor = value ? 1 : 0;
   else if (k == "cache_sinv") ctx->opt_cache_sinv = value ? 1 : 0;
   else if (k == "spectral_jacobi") ctx->opt_spectral_jacobi = value ? 1 : 0;
+  else if (k == "overlap") ctx->opt_overlap = value ? 1 : 0;
   else FAIL(TWOACE_E_INVALID, "unknown option %s", key);
   return TWOACE_OK;
 }

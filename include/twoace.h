@@ -254,7 +254,9 @@ int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_para
  * "tensor" (default 1): the two sensing-matrix products of the cluster kernel run as exact int8 tensor-core products
  * (tcgen05, csrc/tc_prod.cuh), 0 = FP64 SIMT products; "cache_sinv" (default 1): the stages of one trial share one
  * (I + A A')^-1 instead of inverting it once per stage; "spectral_jacobi" (default 0): 1 = SpectralInitialize uses the
- * full Jacobi eigendecomposition for every size instead of the leading-eigenpair solver (csrc/tridiag_eig.cuh). */
+ * full Jacobi eigendecomposition for every size instead of the leading-eigenpair solver (csrc/tridiag_eig.cuh);
+ * "overlap" (default 1): the general-kernel group of a mixed InferADMM launch (tiny problems) runs on a second stream
+ * beside the cluster-kernel groups. */
 int twoace_set_option(twoace_ctx* ctx, const char* key, int value);
 /* InferADMM launches that took the shared-memory cluster kernel since context creation. */
 int64_t twoace_fast_launch_count(const twoace_ctx* ctx);

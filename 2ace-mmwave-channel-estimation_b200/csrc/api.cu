@@ -839,7 +839,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   size_t cursor = 0;
   const DevParams prm = make_dev_params(in.p);
   const cd* Abase_all = dense ? d_Arm : ctx->cb_rm;
-  bool use_codes = false;
+  std::vector<char> inst_codes(nb, 0);     // per instance: the 2-bit representation of its A exists
 
   // ---- pre-processing
   {
@@ -858,7 +858,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
     prep_kernel<<<std::min(nb, 8 * ctx->num_sms), NT, 0, ctx->stream>>>(dt, nb, n, in.p.tol_abs);
     CK(cudaGetLastError());
     ctx->launches++;
-    if (dense && try_codes) {   // 2-bit phase codes of every instance's A; all-or-nothing per chunk
+    if (dense && try_codes) {   // 2-bit phase codes of every instance's A (one batched flag read per chunk)
       std::vector<QuantTask> qt(nb);
       for (int b = 0; b < nb; ++b) {
         QuantTask& q = qt[b];
@@ -874,10 +874,10 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       std::vector<int> flags(nb);
       CK(cudaMemcpyAsync(flags.data(), base + o_qflag, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      use_codes = true;
-      for (int b = 0; b < nb; ++b) use_codes = use_codes && flags[b] == 1;
+      // decided per instance: the kernel an instance runs on never depends on its batch mates
+      for (int b = 0; b < nb; ++b) inst_codes[b] = flags[b] == 1;
     } else if (!dense && try_codes) {
-      use_codes = ctx->cb_codes != nullptr;
+      std::fill(inst_codes.begin(), inst_codes.end(), (char)(ctx->cb_codes != nullptr));
     }
     fill_nan_kernel<<<std::min(4 * ctx->num_sms, (int)(((size_t)nb * n + 255) / 256)), 256, 0, ctx->stream>>>(d_xmax, (size_t)nb * n);
     CK(cudaGetLastError());
@@ -922,6 +922,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.active = pass ? &d_ctl[b].need_r1 : nullptr; a.active_expect = 1;
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
         a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass) * in.p.maxiter : nullptr;
+        const bool use_codes = inst_codes[b] != 0;
         a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
         a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
         if (use_codes && sv_off[b + 1] > sv_off[b]) { a.sinv = (cd*)(base + o_sinv) + sv_off[b]; a.sinv_state = pass ? 1 : 0; }
@@ -975,6 +976,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.active = refine_if_good ? &d_ctl[b].refine_on : nullptr; a.active_expect = 1;
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
       a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + (nstage - 1)) * in.p.maxiter : nullptr;
+      const bool use_codes = inst_codes[b] != 0;
       a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
       a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
       FinalTask& f = ft[b];
@@ -1334,7 +1336,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     CK(cudaGetLastError());
     ctx->launches++;
   }
-  bool use_codes = false;
+  std::vector<char> inst_codes(nb, 0);
   if (try_codes) {
     std::vector<QuantTask> qt(nb);
     for (int b = 0; b < nb; ++b) {
@@ -1350,12 +1352,12 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     std::vector<int> flags(nb);
     CK(cudaMemcpyAsync(flags.data(), base + o_qflag, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    use_codes = true;
-    for (int b = 0; b < nb; ++b) use_codes = use_codes && flags[b] == 1;
+    for (int b = 0; b < nb; ++b) inst_codes[b] = flags[b] == 1;      // per instance
   }
   std::vector<StageTask> tasks(nb);
   for (int b = 0; b < nb; ++b) {
     StageTask& a = tasks[b];
+    const bool use_codes = inst_codes[b] != 0;
     a.codes = use_codes ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : nullptr;
     a.cscale = use_codes ? (const double*)(base + o_mag) + b : nullptr;
     a.A.base = d_Arm + a_off[b]; a.A.rows = nullptr; a.A.scale = d_one;

@@ -235,9 +235,8 @@ __device__ inline void run_big(const StageTask& tk, const DevParams& prm, const 
     }
     __threadfence();
     cl_sync<CS>();
-    if (rank == 0) spd_inverse(U, FN, sm.WT, sm.WT + FN);
-    __threadfence();
-    cl_sync<CS>();
+    // Gauss-Jordan with the columns split over the cluster: one cluster barrier per pivot step
+    spd_inverse_part(U, FN, sm.WT, sm.WT + FN, rank, CS, [] { __threadfence(); cl_sync<CS>(); });
   }
 
   // ---- X = X0 (own columns), M = N = 0

@@ -737,39 +737,59 @@ __device__ inline int block_jacobi_heig(cd* G, int ldg, cd* V, int ldv, int d, c
 // In-place inverse of a d x d Hermitian positive-definite matrix (Gauss-Jordan, no pivoting).
 // S column-major with leading dimension d (generic pointer).  colk/rowk: shared scratch [d] each.
 // Replaces inv(A'*A + eye(n)) at inferLowRankV4.m:221,267 (or its Woodbury core I + A*A').
-__device__ inline void spd_inverse(cd* S, int d, cd* colk, cd* rowk) {
+// The columns can be split over `nparts` cooperating CTAs (a cluster): part p updates columns [d p / nparts,
+// d (p + 1) / nparts) of every pivot step and `sync_all()` (a cluster barrier that also orders global memory) separates
+// the steps; with nparts = 1 it is a block barrier.  One thread owns one row per pass, walks its columns four at a time
+// (independent load / FMA / store chains: the matrix lives in L2, so the step time is load latency over the number of
+// loads in flight) and keeps its pivot-column entry in a register.  Element arithmetic as in the textbook update, so the
+// result does not depend on the split.
+template <class SyncF>
+__device__ inline void spd_inverse_part(cd* S, int d, cd* colk, cd* rowk, int part, int nparts, SyncF sync_all) {
   const int tid = threadIdx.x;
+  const int j0 = (int)((long long)d * part / nparts), j1 = (int)((long long)d * (part + 1) / nparts);
   for (int k = 0; k < d; ++k) {
-    // save pivot row and column
-    for (int i = tid; i < d; i += NT) {
-      colk[i] = S[i + (size_t)d * k];
-      rowk[i] = S[k + (size_t)d * i];
+    for (int i = tid; i < d; i += NT) {      // (L2 loads: with nparts > 1 other CTAs wrote these entries in the last step)
+      colk[i] = __ldcg(S + i + (size_t)d * k);
+      rowk[i] = __ldcg(S + k + (size_t)d * i);
     }
     __syncthreads();
     const cd pv = colk[k];
     // 1/pv (pivot is real positive for an HPD matrix up to rounding; keep it complex for safety)
     const double den = cabs2(pv);
     const cd ip = cmk(pv.x / den, -pv.y / den);
-    for (int idx = tid; idx < d * d; idx += NT) {
-      int i = idx % d, j = idx / d;
-      cd v;
-      if (i == k && j == k) {
-        v = ip;
-      } else if (i == k) {
-        v = cmul(rowk[j], ip);
-      } else if (j == k) {
-        cd t = cmul(colk[i], ip);
-        v = cmk(-t.x, -t.y);
+    for (int i = tid; i < d; i += NT) {
+      cd* row = S + i;
+      if (i == k) {
+        for (int j = j0; j < j1; ++j) row[(size_t)d * j] = (j == k) ? ip : cmul(rowk[j], ip);
       } else {
-        cd f = cmul(colk[i], ip);
-        cd cur = S[idx];
-        cd rj = rowk[j];
-        v = cmk(cur.x - (f.x * rj.x - f.y * rj.y), cur.y - (f.x * rj.y + f.y * rj.x));
+        const cd f = cmul(colk[i], ip);
+        int j = j0;
+        for (; j + 3 < j1; j += 4) {
+          const cd c0 = row[(size_t)d * j], c1 = row[(size_t)d * (j + 1)], c2 = row[(size_t)d * (j + 2)], c3 = row[(size_t)d * (j + 3)];
+          const cd r0 = rowk[j], r1 = rowk[j + 1], r2 = rowk[j + 2], r3 = rowk[j + 3];
+          cd v0 = cmk(c0.x - (f.x * r0.x - f.y * r0.y), c0.y - (f.x * r0.y + f.y * r0.x));
+          cd v1 = cmk(c1.x - (f.x * r1.x - f.y * r1.y), c1.y - (f.x * r1.y + f.y * r1.x));
+          cd v2 = cmk(c2.x - (f.x * r2.x - f.y * r2.y), c2.y - (f.x * r2.y + f.y * r2.x));
+          cd v3 = cmk(c3.x - (f.x * r3.x - f.y * r3.y), c3.y - (f.x * r3.y + f.y * r3.x));
+          if (k >= j && k < j + 4) {
+            const cd nf = cmk(-f.x, -f.y);
+            if (k == j) v0 = nf; else if (k == j + 1) v1 = nf; else if (k == j + 2) v2 = nf; else v3 = nf;
+          }
+          row[(size_t)d * j] = v0; row[(size_t)d * (j + 1)] = v1; row[(size_t)d * (j + 2)] = v2; row[(size_t)d * (j + 3)] = v3;
+        }
+        for (; j < j1; ++j) {
+          const cd cur = row[(size_t)d * j], rj = rowk[j];
+          row[(size_t)d * j] = (j == k) ? cmk(-f.x, -f.y)
+                                        : cmk(cur.x - (f.x * rj.x - f.y * rj.y), cur.y - (f.x * rj.y + f.y * rj.x));
+        }
       }
-      S[idx] = v;
     }
-    __syncthreads();
+    sync_all();
   }
+}
+
+__device__ inline void spd_inverse(cd* S, int d, cd* colk, cd* rowk) {
+  spd_inverse_part(S, d, colk, rowk, 0, 1, [] { __syncthreads(); });
 }
 
 }  // namespace twoace

@@ -943,7 +943,7 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
     if constexpr (TC) tc_build(tc, tg, sm.cik, m, tg.resident ? 0 : rank, tg.resident ? 1 : CS);
     __threadfence();
     cl_sync<CS>();
-    if (rank == 0 && !sinv_reuse) spd_inverse(Sinv, m, scratch, scratch + m);
+    if (!sinv_reuse) spd_inverse_part(Sinv, m, scratch, scratch + m, rank, CS, [] { __threadfence(); cl_sync<CS>(); });
     __threadfence();
     cl_sync<CS>();
   }

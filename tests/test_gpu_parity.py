@@ -471,6 +471,26 @@ def test_general_complex_A_takes_general_kernel(gpu_ctx):
     assert rel(Sg[0]["X"], snap[20]["X"]) < 1e-9
 
 
+def test_dense_batch_kernel_choice_is_per_instance(codebook, gpu_ctx):
+    """Dense mode: a quantised and a non-quantised sensing matrix in ONE batch.  The quantised instance still takes the
+    cluster kernel (the 2-bit decision is per instance), and both results are bitwise those of separate calls."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    rng = np.random.default_rng(5)
+    ins = hz.make_batch(1, codebook, 64, 20.0)[0]
+    A8 = np.exp(1j * np.pi / 8 * rng.integers(0, 16, (64, 256))) / 16
+    B8 = np.abs(A8 @ ins.vecH)
+    tr = ins.train_idx[:1]
+    p = tw.Params.default(maxiter=40).fixed_iters()
+    f0 = gpu_ctx.fast_launch_count
+    both = sv.solve_batch(tw.V4, [ins.A, A8], [ins.B, B8], TX, RX, [tr, tr], p, gpu_ctx)
+    assert gpu_ctx.fast_launch_count > f0                      # the quantised instance ran on the cluster kernel
+    one = sv.solve_batch(tw.V4, [ins.A], [ins.B], TX, RX, [tr], p, gpu_ctx)
+    two = sv.solve_batch(tw.V4, [A8], [B8], TX, RX, [tr], p, gpu_ctx)
+    assert np.array_equal(both.X[0], one.X[0]) and np.array_equal(both.X[1], two.X[0])
+    assert both.quality[0] == one.quality[0] and both.quality[1] == two.quality[0]
+
+
 def _synthetic_case(tx, rx, m, seed, L=3):
     """2-bit random beams (Generate_random_beam.m:31-34) on a tx x rx array, sparse multipath channel."""
     from twoace_b200 import harness as hz

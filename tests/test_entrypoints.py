@@ -58,9 +58,14 @@ def test_a2only_and_multires_entry_points_against_oracle(gpu_ctx):
         Xo, _, _ = admm.infer_low_rank_v4_multi(cb[rows], B, 16, 16, po, train_idx=list(tr))
         Xp, _, _ = admm.infer_low_rank_v4_multi(cb[rows], B * (1 + 1e-14 * rng.standard_normal(B.shape)), 16, 16, po,
                                                 train_idx=list(tr))
-        if hz.aligned_rel_err(Xp, Xo) <= 1e-6:                   # reference-determined (see test_gpu_parity.py)
-            assert hz.aligned_rel_err(H[k] * ep.RSS_FCT, Xo) < 1e-4
+        self_sens = hz.aligned_rel_err(Xp, Xo)
+        err = hz.aligned_rel_err(H[k] * ep.RSS_FCT, Xo)
+        if self_sens <= 1e-6:                                    # reference-determined (see test_gpu_parity.py)
+            assert err < 1e-4
             n_checked += 1
+        else:                                                    # noise-decided in the reference itself: 100x its own response
+            assert err <= max(1e-4, 100 * self_sens)
+    assert n_checked >= 1, "no reference-determined instance among M = 36 / 121 / 225"
     assert np.all(np.isfinite(H))                                 # NaN -> 0 (A2only.m:176)
 
 

@@ -111,7 +111,7 @@ def _oracle_worker(job):
     from oracle import admm
     variant, A, B, train_idx = job[:4]
     TX, RX = job[4] if len(job) > 4 else (16, 16)
-    p = admm.Params().fixed_iters()
+    p = admm.Params() if (len(job) > 6 and job[6]) else admm.Params().fixed_iters()
     with threadpool_limits(limits=1):
         t0 = time.perf_counter()
         if variant == "NUCLEAR":
@@ -124,12 +124,12 @@ def _oracle_worker(job):
     return X, dt, (job[5] if len(job) > 5 else -1)
 
 
-def run_oracle_pool(variant, insts, cores, dims=(16, 16)):
+def run_oracle_pool(variant, insts, cores, dims=(16, 16), default_tol=False):
     """Time the NumPy oracle on `insts`, trial-parallel over `cores` single-threaded processes
     (the analogue of the reference's parfor, Vs_M_par.m:145).  Returns (X list, wall seconds)."""
     import multiprocessing as mp
     order = sorted(range(len(insts)), key=lambda k: -len(insts[k].B))      # longest first
-    jobs = [(variant, insts[k].A, insts[k].B, insts[k].train_idx, dims, k) for k in order]
+    jobs = [(variant, insts[k].A, insts[k].B, insts[k].train_idx, dims, k, default_tol) for k in order]
     ctx = mp.get_context("spawn")
     out = [None] * len(insts)
     with ctx.Pool(cores) as pool:
@@ -288,7 +288,9 @@ def ours_arm(args, wl, rank, local_rank, world):
     TX, RX = wl.get("tx", 16), wl.get("rx", 16)
     N = TX * RX
     tpc = args.trials_per_cell
-    p = tw.Params.default().fixed_iters()
+    if args.strong:            # strong scaling: the single-GPU batch is divided over the ranks
+        tpc = max(1, math.ceil(tpc / world))
+    p = tw.Params.default() if args.default_tolerances else tw.Params.default().fixed_iters()
     nstage = 4 * T + 1
     row_scale = 1.0 / math.sqrt(N)
     dense = bool(args.dense) or N != 256
@@ -418,6 +420,10 @@ def ours_arm(args, wl, rank, local_rank, world):
                 "traffic": 9.67e6 if (N == 256 and wl["variant"] == "NUCLEAR") else None,
                 "traffic_source": "profiles/r02_fast_stage_nuclear_cs4_tc_ncu_full_summary.csv (bytes per launch of 33 "
                                   "tasks x 40 iterations; the iteration kernels are not HBM-bound: L2 hit rate 99.4 %)",
+                # what ncu measured for the same kernel (committed capture, not live): the contract fraction above credits
+                # flops the kernel does not execute on the FP64 pipe (tensor-core products, screened eigensolves)
+                "ncu_fp64_pipe_active_pct": 5.97 if (N == 256 and wl["variant"] == "NUCLEAR") else None,
+                "ncu_barrier_stall_per_issue": 12.5 if (N == 256 and wl["variant"] == "NUCLEAR") else None,
                 "kernel": "InferADMM stage kernels (fast_stage_kernel<RL,CS> / big_stage_kernel / big1_stage_kernel where "
                           "eligible, else admm_stage_kernel)",
                 "fast_kernel_launches": int(ctx.fast_launch_count), "kernel_ms_per_step": stage_ms / args.steps,
@@ -500,7 +506,7 @@ def ours_arm(args, wl, rank, local_rank, world):
                 o = osyn.synth_instance(cb, int(m[i]), float(snr[i]), int(lo[i]), int(hi[i]), int(tid[i]), nt=TX, nr=RX,
                                         ntrain=T, seed=hz.BASE_SEED)
                 sub.append(hz.Instance(o["rows"], cb[o["rows"]] * row_scale, o["B"], o["train_idx"], o["vecH"], float(snr[i])))
-        Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)), (TX, RX))
+        Xo, wall = run_oracle_pool(wl["variant"], sub, min(cores, len(sub)), (TX, RX), args.default_tolerances)
         cpu_baseline = {"value": len(sub) / wall, "unit": "solves/s", "cores": min(cores, len(sub)),
                         "kind": "port",
                         "sample": f"{len(sub)} of the step's {nb} instances ({len(sub) // n_cells} per (M,SNR) cell), "
@@ -512,9 +518,14 @@ def ours_arm(args, wl, rank, local_rank, world):
     if rank == 0:
         line = {"metric": METRIC if N == 256 else METRIC.replace("16x16", f"{TX}x{RX}"), "value": value,
                 "unit": "solves/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["desc"], "fixed_iters": 500, "solves_per_step_per_gpu": nb,
+                "config": {"workload": wl["desc"],
+                           "fixed_iters": None if args.default_tolerances else 500,
+                           "tolerances": "reference defaults (tol_rel 1e-4, tol_abs 1e-8, maxiter 500)" if args.default_tolerances
+                                         else "0 (fixed-iteration mode, SURVEY 8d)",
+                           "solves_per_step_per_gpu": nb,
                            "trials_per_cell_per_gpu": tpc, "cells": n_cells,
                            "input_mode": "dense complex128 A per instance, instances built on the host" if dense else
                                          "codebook rows (codebook registered once); instances built on the device by "
@@ -739,6 +750,11 @@ def main():
     ap.add_argument("--fast-cs", type=int, default=None, help="cluster size of the r=20 stages (2 or 4)")
     ap.add_argument("--no-fast", action="store_true", help="force the general kernel")
     ap.add_argument("--dense", action="store_true", help="ship a dense complex128 A per instance instead of codebook rows")
+    ap.add_argument("--default-tolerances", action="store_true",
+                    help="run the solvers with the reference's default tolerances instead of the fixed-iteration mode of "
+                         "the headline metric (the reference's own operating mode: no caller passes tolerances)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: divide the single-GPU batch over the ranks instead of giving every rank its own")
     ap.add_argument("--dedup-nuclear-rerun", action="store_true",
                     help="opt-in exact elision of the bit-identical rank-one rerun of inferLowRank_Nuclear "
                          "(not the default measurement: the literal reference flow is)")

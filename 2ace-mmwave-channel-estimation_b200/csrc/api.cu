@@ -49,10 +49,15 @@ struct twoace_ctx {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events;
   std::vector<std::string> stage_labels;   // one per stage_events entry (TWOACE_TRACE_LAUNCHES=1 prints them)
-  cudaStream_t side_stream = nullptr;      // tiny general-kernel groups of a stage run here, beside the cluster kernels
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  DevBuf ws_side;                          // workspace of the side stream
-  bool in_side = false;
+  // The kernel groups of one InferADMM stage launch (different cluster shapes / kernels for different m) run
+  // concurrently: the first on the main stream, the others on side streams, each with its own workspace.
+  static constexpr int NSIDE = 4;
+  cudaStream_t side_stream[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  DevBuf ws_side[NSIDE];
+  bool in_side = false;                    // inside a concurrent launch group: per-kernel events are not summed
+  DevBuf counters;                         // task-queue counters of the cluster kernels (ring of NCOUNTER ints)
+  int counter_cursor = 0;
   int opt_overlap = 1;                     // 1: overlap the general-kernel group of a stage with its cluster-kernel groups
   std::vector<char> stage_side;            // per stage_events entry: 1 = ran on the side stream (not summed)
   std::vector<std::pair<void*, size_t>> stage_cache;   // free device buffers of the host-pointer staging (pointer, capacity)
@@ -128,11 +133,13 @@ extern "C" int twoace_create(int device, twoace_ctx** out) {
     delete ctx;
     return TWOACE_E_CUDA;
   }
-  if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+  bool side_ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < twoace_ctx::NSIDE && side_ok; ++k)
+    side_ok = cudaStreamCreateWithFlags(&ctx->side_stream[k], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!side_ok) {
     (void)cudaGetLastError();
-    ctx->side_stream = nullptr;     // overlap disabled; everything runs on the main stream
+    ctx->side_stream[0] = nullptr;     // overlap disabled; everything runs on the main stream
   }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
@@ -153,10 +160,13 @@ extern "C" void twoace_destroy(twoace_ctx* ctx) {
   if (ctx->cb_rm) cudaFree(ctx->cb_rm);
   if (ctx->cb_codes) cudaFree(ctx->cb_codes);
   for (auto& pr : ctx->stage_cache) cudaFree(pr.first);
-  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  for (int k = 0; k < twoace_ctx::NSIDE; ++k) {
+    if (ctx->side_stream[k]) { cudaStreamSynchronize(ctx->side_stream[k]); cudaStreamDestroy(ctx->side_stream[k]); }
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    if (ctx->ws_side[k].p) cudaFree(ctx->ws_side[k].p);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->ws_side.p) cudaFree(ctx->ws_side.p);
+  if (ctx->counters.p) cudaFree(ctx->counters.p);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -267,6 +277,26 @@ static int stage_grid(twoace_ctx* ctx, size_t smem, int ntasks, int* grid) {
 }
 
 constexpr size_t SMEM_LIMIT = (size_t)227 * 1024;
+constexpr int NCOUNTER = 256;
+
+static void push_stage_event(twoace_ctx* ctx, cudaEvent_t e0, cudaEvent_t e1, const char* label, bool group = false) {
+  ctx->stage_events.emplace_back(e0, e1);
+  std::string lb(label);
+  if (ctx->in_side && !group) lb += "  (inside the concurrent group below: not summed)";
+  ctx->stage_labels.emplace_back(lb);
+  ctx->stage_side.resize(ctx->stage_events.size(), 0);
+  ctx->stage_side.back() = (ctx->in_side && !group) ? 1 : 0;
+}
+
+// A zeroed task-queue counter for the next cluster-kernel launch on the context's current stream.
+static int next_counter(twoace_ctx* ctx, int** out) {
+  int rc = ensure(ctx, ctx->counters, NCOUNTER * sizeof(int));
+  if (rc) return rc;
+  int* p = (int*)ctx->counters.p + (ctx->counter_cursor++ % NCOUNTER);
+  CK(cudaMemsetAsync(p, 0, sizeof(int), ctx->stream));
+  *out = p;
+  return 0;
+}
 
 template <int RL, int CS, bool TC>
 static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const DevParams& prm, FastDims fd,
@@ -302,14 +332,16 @@ static int launch_fast_t(twoace_ctx* ctx, const StageTask* dt, int ntasks, const
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
   }
-  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p));
+  int* counter = nullptr;
+  rc = next_counter(ctx, &counter);
+  if (rc) return rc;
+  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p, counter));
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
     snprintf(lb, sizeof lb, "fast_stage_kernel<%d,%d,%s> tasks %d clusters %d maxm %d smem %zu nslot %d n1 %d", RL, CS,
              TC ? "tc" : "simt", ntasks, ncl, fd.maxm, smem, fd.tc.nslot, fd.tc.n1);
-    ctx->stage_labels.emplace_back(lb);
+    push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
   ctx->fast_launches++;
@@ -349,14 +381,16 @@ static int launch_big(twoace_ctx* ctx, const StageTask* dt, int ntasks, const De
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
   }
-  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p));
+  int* counter = nullptr;
+  rc = next_counter(ctx, &counter);
+  if (rc) return rc;
+  CK(cudaLaunchKernelEx(&cfg, kern, dt, ntasks, prm, fd, (cd*)ctx->ws.p, counter));
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
     snprintf(lb, sizeof lb, "big_stage_kernel tasks %d clusters %d mfull %d smem %zu nslot %d n1 %d", ntasks, ncl, fd.mfull,
              smem, fd.tc.nslot, fd.tc.n1);
-    ctx->stage_labels.emplace_back(lb);
+    push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
   ctx->fast_launches++;
@@ -389,10 +423,9 @@ static int launch_big1(twoace_ctx* ctx, const StageTask* dt, int ntasks, const D
   CK(cudaGetLastError());
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
     snprintf(lb, sizeof lb, "big1_stage_kernel tasks %d grid %d (x%d per SM) maxm %d smem %zu", ntasks, grid, occ, fd.maxm, smem);
-    ctx->stage_labels.emplace_back(lb);
+    push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
   ctx->fast_launches++;
@@ -450,13 +483,9 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
   CK(cudaGetLastError());
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
-    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d%s", tasks.size(), grid, dm.maxm, dm.maxr,
-             ctx->in_side ? " (side stream, overlaps the launches below)" : "");
-    ctx->stage_labels.emplace_back(lb);
-    ctx->stage_side.resize(ctx->stage_events.size(), 0);
-    ctx->stage_side.back() = ctx->in_side ? 1 : 0;
+    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d", tasks.size(), grid, dm.maxm, dm.maxr);
+    push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
   return 0;
@@ -491,10 +520,9 @@ static int launch_minl2(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
   CK(cudaGetLastError());
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
     char lb[160];
     snprintf(lb, sizeof lb, "minl2_stage_kernel tasks %d grid %d maxm %d maxr %d", (int)tasks.size(), grid, dm.maxm, dm.maxr);
-    ctx->stage_labels.emplace_back(lb);
+    push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
   return 0;
@@ -540,83 +568,133 @@ static int launch_stage(twoace_ctx* ctx, const std::vector<StageTask>& tasks, co
     else if (f2) grp[2].push_back(t);
     else gen.push_back(t);
   }
-  // The general-kernel group of a mixed launch (tiny problems such as M = 4: a few dozen latency-bound CTAs) runs on the
-  // side stream with its own workspace, beside the cluster-kernel groups, which leave SMs free (132 of 148 for CS = 4).
-  bool gen_forked = false;
-  if (ctx->opt_overlap && ctx->side_stream && !gen.empty() && gen.size() < tasks.size()) {
+  // The groups of a mixed launch are independent (different instances): they run concurrently -- the first on the
+  // main stream, the others on side streams with their own workspaces -- and the cluster kernels take their tasks
+  // from a device counter, so a group that gets SMs late simply processes what is left.  One group leaves SMs idle
+  // (132 of 148 for clusters of 4, far fewer for a handful of tiny problems); together they fill the machine.
+  int ngroups = (big.empty() ? 0 : 1) + (big1.empty() ? 0 : 1) + (gen.empty() ? 0 : 1);
+  for (int g = 0; g < 5; ++g) ngroups += grp[g].empty() ? 0 : 1;
+  const bool concurrent = ctx->opt_overlap && ctx->side_stream[0] != nullptr && ngroups >= 2;
+  int slot = 0;
+  bool side_used[twoace_ctx::NSIDE] = {false, false, false, false};
+  cudaEvent_t g0 = nullptr, g1 = nullptr;
+  if (concurrent) {
+    if (ctx->timing) {
+      CK(cudaEventCreate(&g0));
+      CK(cudaEventCreate(&g1));
+      CK(cudaEventRecord(g0, ctx->stream));
+    }
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-    std::swap(ctx->stream, ctx->side_stream);
-    std::swap(ctx->ws, ctx->ws_side);
     ctx->in_side = true;
-    int rc = launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
-    cudaError_t e = rc ? cudaSuccess : cudaEventRecord(ctx->ev_join, ctx->stream);
-    ctx->in_side = false;
-    std::swap(ctx->ws, ctx->ws_side);
-    std::swap(ctx->stream, ctx->side_stream);
-    if (rc) return rc;
-    if (e != cudaSuccess) FAIL(TWOACE_E_CUDA, "cudaEventRecord on the side stream failed: %s", cudaGetErrorString(e));
-    gen_forked = true;
   }
-  for (int g = 0; g < 5; ++g) {
+  auto run_group = [&](auto&& fn) -> int {
+    const int my = slot++;
+    if (!concurrent || my == 0) return fn();
+    const int k = (my - 1) % twoace_ctx::NSIDE;
+    if (!side_used[k]) {
+      if (cudaStreamWaitEvent(ctx->side_stream[k], ctx->ev_fork, 0) != cudaSuccess) { ctx->err = "cudaStreamWaitEvent failed"; return TWOACE_E_CUDA; }
+      side_used[k] = true;
+    }
+    std::swap(ctx->stream, ctx->side_stream[k]);
+    std::swap(ctx->ws, ctx->ws_side[k]);
+    const int rc = fn();
+    std::swap(ctx->ws, ctx->ws_side[k]);
+    std::swap(ctx->stream, ctx->side_stream[k]);
+    return rc;
+  };
+  auto finish = [&](int rc) -> int {
+    if (!concurrent) return rc;
+    ctx->in_side = false;
+    for (int k = 0; k < twoace_ctx::NSIDE; ++k) {
+      if (!side_used[k]) continue;
+      if (cudaEventRecord(ctx->ev_join[k], ctx->side_stream[k]) != cudaSuccess ||
+          cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0) != cudaSuccess) {
+        if (!rc) { ctx->err = "joining the side streams failed"; rc = TWOACE_E_CUDA; }
+      }
+    }
+    if (g0) {
+      if (!rc && cudaEventRecord(g1, ctx->stream) == cudaSuccess) {
+        char lb[96];
+        snprintf(lb, sizeof lb, "launch group: the %d kernels above, concurrently", ngroups);
+        push_stage_event(ctx, g0, g1, lb, true);
+      } else {
+        cudaEventDestroy(g0);
+        cudaEventDestroy(g1);
+      }
+    }
+    return rc;
+  };
+  int rc = 0;
+  if (!big.empty()) {
+    rc = run_group([&]() -> int {
+      std::stable_sort(big.begin(), big.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
+      FastDims fd = {};
+      fd.maxm = BIG_CH; fd.mw = BIG_CH / 16; fd.r = BIG_R; fd.ws_stride = 0; fd.nuclear = 0; fd.ds = 16;
+      fd.mfull = big.front().m;
+      if (!fast_tc_layout<BIG_RL>(fd, SMEM_LIMIT)) FAIL(TWOACE_E_CUDA, "internal: chunked cluster kernel layout (mfull %d)", fd.mfull);
+      const StageTask* dt = nullptr;
+      int r2 = upload_tasks(ctx, big, cursor, &dt);
+      if (r2) return r2;
+      bool launched = false;
+      r2 = launch_big(ctx, dt, (int)big.size(), prm, fd, &launched);
+      if (r2) return r2;
+      if (!launched) FAIL(TWOACE_E_CUDA, "chunked cluster kernel launch configuration rejected (mfull %d)", fd.mfull);
+      return 0;
+    });
+    if (rc) return finish(rc);
+  }
+  const int order[5] = {1, 3, 0, 2, 4};     // clusters of 4 first: they need four free SMs of one GPC
+  for (int gi = 0; gi < 5; ++gi) {
+    const int g = order[gi];
     std::vector<StageTask>& ft = grp[g];
     if (ft.empty()) continue;
-    // longest tasks first: clusters pick tasks round-robin, so this balances the tail of the launch
-    std::stable_sort(ft.begin(), ft.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
-    int maxm = 1;
-    for (const StageTask& t : ft) maxm = std::max(maxm, t.m);
-    FastDims fd = {};
-    bool ok = true;
-    if (g == 4) {
-      fd.maxm = maxm; fd.mw = (maxm + 15) / 16; fd.r = 1; fd.ws_stride = 0; fd.nuclear = nuc ? 1 : 0; fd.ds = 16;
-    } else if (g == 0 || g == 2) ok = fast_dims<10>(maxm, nuc, g == 0, &fd);
-    else ok = fast_dims<5>(maxm, nuc, g == 1, &fd);
-    if (!ok) FAIL(TWOACE_E_CUDA, "internal: cluster kernel layout (group %d, maxm %d)", g, maxm);
-    const StageTask* dt = nullptr;
-    int rc = upload_tasks(ctx, ft, cursor, &dt);
-    if (rc) return rc;
-    bool launched = false;
-    switch (g) {
-      case 0: rc = launch_fast_t<10, 2, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
-      case 1: rc = launch_fast_t<5, 4, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
-      case 2: rc = launch_fast_t<10, 2, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
-      case 3: rc = launch_fast_t<5, 4, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
-      default: rc = launch_fast_t<1, 1, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
-    }
-    if (rc) return rc;
-    if (!launched) FAIL(TWOACE_E_CUDA, "cluster kernel launch configuration rejected (group %d, maxm %d)", g, fd.maxm);
-  }
-  if (!big.empty()) {
-    std::stable_sort(big.begin(), big.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
-    FastDims fd = {};
-    fd.maxm = BIG_CH; fd.mw = BIG_CH / 16; fd.r = BIG_R; fd.ws_stride = 0; fd.nuclear = 0; fd.ds = 16;
-    fd.mfull = big.front().m;
-    if (!fast_tc_layout<BIG_RL>(fd, SMEM_LIMIT)) FAIL(TWOACE_E_CUDA, "internal: chunked cluster kernel layout (mfull %d)", fd.mfull);
-    const StageTask* dt = nullptr;
-    int rc = upload_tasks(ctx, big, cursor, &dt);
-    if (rc) return rc;
-    bool launched = false;
-    rc = launch_big(ctx, dt, (int)big.size(), prm, fd, &launched);
-    if (rc) return rc;
-    if (!launched) FAIL(TWOACE_E_CUDA, "chunked cluster kernel launch configuration rejected (mfull %d)", fd.mfull);
+    rc = run_group([&]() -> int {
+      // longest tasks first: the queue hands them out in this order, which balances the tail of the launch
+      std::stable_sort(ft.begin(), ft.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
+      int maxm = 1;
+      for (const StageTask& t : ft) maxm = std::max(maxm, t.m);
+      FastDims fd = {};
+      bool ok = true;
+      if (g == 4) {
+        fd.maxm = maxm; fd.mw = (maxm + 15) / 16; fd.r = 1; fd.ws_stride = 0; fd.nuclear = nuc ? 1 : 0; fd.ds = 16;
+      } else if (g == 0 || g == 2) ok = fast_dims<10>(maxm, nuc, g == 0, &fd);
+      else ok = fast_dims<5>(maxm, nuc, g == 1, &fd);
+      if (!ok) FAIL(TWOACE_E_CUDA, "internal: cluster kernel layout (group %d, maxm %d)", g, maxm);
+      const StageTask* dt = nullptr;
+      int r2 = upload_tasks(ctx, ft, cursor, &dt);
+      if (r2) return r2;
+      bool launched = false;
+      switch (g) {
+        case 0: r2 = launch_fast_t<10, 2, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+        case 1: r2 = launch_fast_t<5, 4, true>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+        case 2: r2 = launch_fast_t<10, 2, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+        case 3: r2 = launch_fast_t<5, 4, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+        default: r2 = launch_fast_t<1, 1, false>(ctx, dt, (int)ft.size(), prm, fd, &launched); break;
+      }
+      if (r2) return r2;
+      if (!launched) FAIL(TWOACE_E_CUDA, "cluster kernel launch configuration rejected (group %d, maxm %d)", g, fd.maxm);
+      return 0;
+    });
+    if (rc) return finish(rc);
   }
   if (!big1.empty()) {
-    std::stable_sort(big1.begin(), big1.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
-    FastDims fd = {};
-    fd.maxm = big1.front().m; fd.mw = (fd.maxm + 15) / 16; fd.r = 1; fd.ds = 16; fd.lean = 1;
-    const StageTask* dt = nullptr;
-    int rc = upload_tasks(ctx, big1, cursor, &dt);
-    if (rc) return rc;
-    bool launched = false;
-    rc = launch_big1(ctx, dt, (int)big1.size(), prm, fd, &launched);
-    if (rc) return rc;
-    if (!launched) FAIL(TWOACE_E_CUDA, "r = 1 large-m kernel launch configuration rejected (maxm %d)", fd.maxm);
+    rc = run_group([&]() -> int {
+      std::stable_sort(big1.begin(), big1.end(), [](const StageTask& a, const StageTask& b) { return a.m > b.m; });
+      FastDims fd = {};
+      fd.maxm = big1.front().m; fd.mw = (fd.maxm + 15) / 16; fd.r = 1; fd.ds = 16; fd.lean = 1;
+      const StageTask* dt = nullptr;
+      int r2 = upload_tasks(ctx, big1, cursor, &dt);
+      if (r2) return r2;
+      bool launched = false;
+      r2 = launch_big1(ctx, dt, (int)big1.size(), prm, fd, &launched);
+      if (r2) return r2;
+      if (!launched) FAIL(TWOACE_E_CUDA, "r = 1 large-m kernel launch configuration rejected (maxm %d)", fd.maxm);
+      return 0;
+    });
+    if (rc) return finish(rc);
   }
-  if (gen_forked) {      // join: later launches on the main stream see the side stream's results
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    return 0;
-  }
-  return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor);
+  if (!gen.empty()) rc = run_group([&]() -> int { return launch_stage_general(ctx, gen, prm, n, tx, rx, cursor); });
+  return finish(rc);
 }
 
 static int launch_spectral(twoace_ctx* ctx, const std::vector<SpecTask>& tasks, int n, size_t& cursor) {
@@ -1540,7 +1618,7 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
   ctx->launches++;
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
-    ctx->stage_events.emplace_back(e0, e1);
+    push_stage_event(ctx, e0, e1, "phaselift_kernel");
   }
   rc = host_back(ctx, mem, sig, dSig, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
   rc = host_back(ctx, mem, info, dInfo, (size_t)nb * PL_INFO * sizeof(double)); if (rc) return rc;

@@ -555,8 +555,9 @@ __device__ inline void run_big(const StageTask& tk, const DevParams& prm, const 
 }
 
 __global__ void __launch_bounds__(NT, 1)
-big_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
+big_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase, int* counter) {
   extern __shared__ __align__(1024) unsigned char big_smem_raw[];
+  __shared__ int s_next_task;
   const FastSmem<BIG_RL> sm = fast_carve<BIG_RL>(big_smem_raw, fd);
   const int rank = (int)cg::this_cluster().block_rank();
   const int cid = blockIdx.x / BIG_CS, ncl = gridDim.x / BIG_CS;
@@ -573,7 +574,9 @@ big_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm,
   tc.Bs = sm.tc_bs; tc.ov = sm.tc_ov; tc.ex = sm.tc_ex; tc.bars = sm.tc_bars; tc.tmem = *sm.tc_tslot;
   tc.nslot_launch = fd.tc.nslot; tc.nslot = fd.tc.nslot; tc.n1 = fd.tc.n1; tc.slot_bytes = fd.tc.slot_bytes;
   tc.wt = (unsigned char*)sm.WT; tc.wt_slot = -1;
-  for (int t = cid; t < ntasks; t += ncl) {
+  for (int t = cid;; t += ncl) {      // dynamic task queue, see fast_stage_kernel
+    if (counter != nullptr) t = next_task<BIG_CS>(counter, &s_next_task, rank);
+    if (t >= ntasks) break;
     const StageTask tk = tasks[t];
     if (tk.active != nullptr && *tk.active != tk.active_expect) continue;   // cluster-uniform
     run_big(tk, prm, fd, sm, wsg, rank, tc);

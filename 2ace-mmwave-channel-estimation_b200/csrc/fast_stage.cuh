@@ -193,6 +193,16 @@ __device__ __forceinline__ T* peer_ptr(T* p, int rank) {
   else return p;
 }
 
+// Next task index from a device-wide counter, the same value in every CTA of the cluster (two cluster barriers).
+template <int CS>
+__device__ __forceinline__ int next_task(int* counter, int* slot, int rank) {
+  if (rank == 0 && threadIdx.x == 0) *slot = atomicAdd(counter, 1);
+  cl_sync<CS>();
+  const int t = *peer_ptr<int, CS>(slot, 0);
+  cl_sync<CS>();      // rank 0 may overwrite its slot only after every CTA has read it
+  return t;
+}
+
 // A' product, register-tiled 2 (k) x RL (columns) with the reduction over i split over a lane pair:
 //   thread t: s = t & 1, k0 = t >> 1, k1 = k0 + 128, rows i = s, s + 2, s + 4, ...
 // Every operand Op[i, c] loaded from shared memory feeds 8 DFMAs (a broadcast LDS.128 costs 4 cycles of the
@@ -1281,8 +1291,9 @@ __device__ inline void run_fast(const StageTask& tk, const DevParams& prm, const
 
 template <int RL, int CS, bool TC>
 __global__ void __launch_bounds__(NT, (RL == 1) ? 2 : 1)
-fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase) {
+fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, FastDims fd, cd* wsbase, int* counter) {
   extern __shared__ __align__(1024) unsigned char fast_smem_raw[];
+  __shared__ int s_next_task;
   const FastSmem<RL> sm = fast_carve<RL>(fast_smem_raw, fd);
   int rank = 0;
   if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
@@ -1303,7 +1314,11 @@ fast_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm
     tc.nslot_launch = fd.tc.nslot; tc.nslot = fd.tc.nslot; tc.n1 = fd.tc.n1; tc.slot_bytes = fd.tc.slot_bytes;
     tc.wt = (unsigned char*)sm.WT; tc.wt_slot = -1;
   }
-  for (int t = cid; t < ntasks; t += ncl) {
+  // Tasks are handed out through a device counter (longest first): a cluster that starts late -- the launch may share
+  // the GPU with the other kernel groups of its stage -- simply takes fewer of them.  counter == nullptr: round robin.
+  for (int t = cid;; t += ncl) {
+    if (counter != nullptr) t = next_task<CS>(counter, &s_next_task, rank);
+    if (t >= ntasks) break;
     const StageTask tk = tasks[t];
     if (tk.active != nullptr && *tk.active != tk.active_expect) continue;   // cluster-uniform
     run_fast<RL, CS, TC>(tk, prm, fd, sm, wsg, rank, tc);

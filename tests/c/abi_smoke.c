@@ -71,6 +71,43 @@ int main(int argc, char** argv) {
   /* error path: bad variant must fail with a message, and the context must stay usable */
   rc = twoace_solve_batch(ctx, 99, TWOACE_MEM_HOST, 1, TX, RX, &m, A, B, train, &p, X, Y, &quality, NULL, NULL);
   if (rc != TWOACE_E_INVALID || strlen(twoace_last_error(ctx)) == 0) { printf("FAIL error path\n"); return 7; }
+  /* the simulation pipeline without per-instance host data: register the sensing rows as a codebook, build instances on
+   * the GPU (twoace_synth_batch), solve them in codebook mode, evaluate (Evaluation_H.m, Evaluation_Recovery.m) */
+  {
+    enum { NB = 3, MS = 24 };
+    static double cb[2 * M * N];
+    for (int i = 0; i < 2 * M * N; ++i) cb[i] = A[i] * 4.0;          /* unit-modulus 4-phase entries, column-major M x N */
+    rc = twoace_set_codebook(ctx, TWOACE_MEM_HOST, M, N, cb);
+    if (rc != TWOACE_OK) { printf("FAIL set_codebook: %s\n", twoace_last_error(ctx)); return 8; }
+    twoace_synth_params sp;
+    twoace_synth_default_params(&sp, TX, RX);
+    int32_t ms[NB] = {MS, MS, MS}, lo[NB] = {0, 0, 0}, hi[NB] = {M, M, M};
+    double snr[NB] = {30.0, 30.0, 30.0};
+    int64_t trial[NB] = {1, 2, 3};
+    static int32_t rows[NB * MS], tr[NB * MS];
+    static double Bs[NB * MS], Hs[2 * NB * N], ang[NB * 6], Xs[2 * NB * N], Ys[2 * NB * MS], qs[NB], mets[NB * TWOACE_METRIC_WORDS],
+        angm[NB * TWOACE_ANGLE_WORDS];
+    rc = twoace_synth_batch(ctx, TWOACE_MEM_HOST, NB, &sp, ms, snr, lo, hi, trial, rows, tr, Bs, Hs, ang);
+    if (rc != TWOACE_OK) { printf("FAIL synth: %s\n", twoace_last_error(ctx)); return 9; }
+    for (int i = 0; i < NB * MS; ++i)
+      if (rows[i] < 0 || rows[i] >= M || !(Bs[i] >= 0.0)) { printf("FAIL synth output\n"); return 10; }
+    rc = twoace_solve_batch_codebook(ctx, TWOACE_V4, TWOACE_MEM_HOST, NB, TX, RX, ms, rows, sp.row_scale, Bs, tr, &p, Xs, Ys, qs,
+                                     NULL, NULL);
+    if (rc != TWOACE_OK) { printf("FAIL codebook solve: %s\n", twoace_last_error(ctx)); return 11; }
+    rc = twoace_metrics_batch(ctx, TWOACE_MEM_HOST, NB, TX, RX, Xs, Hs, 2, mets);
+    if (rc == TWOACE_OK)
+      rc = twoace_angle_metrics_batch(ctx, TWOACE_MEM_HOST, NB, TX, RX, sp.L, 4 * TX, 4 * RX, sp.searching_area, sp.wavelength,
+                                      sp.spacing, Xs, ang, angm);
+    if (rc != TWOACE_OK) { printf("FAIL evaluation: %s\n", twoace_last_error(ctx)); return 12; }
+    printf("synth + codebook solve: quality %.3f %.3f %.3f, MSE_H %.2e, AoDA error %.2f deg\n", qs[0], qs[1], qs[2], mets[0], angm[2]);
+  }
+  /* one context over a set of GPUs (here: the one GPU this client assumes) */
+  {
+    twoace_ctx* mctx = NULL;
+    int dev[1] = {0};
+    if (twoace_create_multi(dev, 1, &mctx) != TWOACE_OK || twoace_device_count(mctx) != 1) { printf("FAIL create_multi\n"); return 13; }
+    twoace_destroy(mctx);
+  }
   twoace_destroy(ctx);
   printf("OK solve\n");
   return 0;

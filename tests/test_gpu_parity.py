@@ -471,6 +471,27 @@ def test_general_complex_A_takes_general_kernel(gpu_ctx):
     assert rel(Sg[0]["X"], snap[20]["X"]) < 1e-9
 
 
+def test_concurrent_launch_groups_do_not_change_results(codebook, gpu_ctx):
+    """A batch that mixes every kernel group of a stage launch (M = 4 general kernel, 36 and 121 cluster kernels of
+    both shapes, 361 large-M kernels): with the groups launched concurrently on side streams and tasks handed out by
+    the device queue (default) the results are bitwise those of the serial launch order (option overlap = 0)."""
+    import twoace_b200 as tw
+    from twoace_b200 import harness as hz, solvers as sv
+    insts = []
+    for M in (4, 36, 121, 361, 36, 4, 121):
+        insts += hz.make_batch(2, codebook, M, 20.0)
+    p = tw.Params.default(maxiter=40).fixed_iters()
+    args = ([i.A for i in insts], [i.B for i in insts], TX, RX, [i.train_idx[:3] for i in insts], p, gpu_ctx)
+    a = sv.solve_batch(tw.V4_MULTI, *args)
+    gpu_ctx.set_option("overlap", 0)
+    try:
+        b = sv.solve_batch(tw.V4_MULTI, *args)
+    finally:
+        gpu_ctx.set_option("overlap", 1)
+    assert np.array_equal(a.X, b.X, equal_nan=True) and np.array_equal(a.quality, b.quality, equal_nan=True)
+    assert np.array_equal(a.info, b.info, equal_nan=True)
+
+
 def test_dense_batch_kernel_choice_is_per_instance(codebook, gpu_ctx):
     """Dense mode: a quantised and a non-quantised sensing matrix in ONE batch.  The quantised instance still takes the
     cluster kernel (the 2-bit decision is per instance), and both results are bitwise those of separate calls."""

@@ -192,9 +192,7 @@ extern "C" int twoace_create_multi(const int* devices, int n_dev, twoace_ctx** o
   if (!out) return TWOACE_E_INVALID;
   *out = nullptr;
   if (!devices || n_dev < 1) return TWOACE_E_INVALID;
-  for (int i = 0; i < n_dev; ++i)
-    for (int j = 0; j < i; ++j)
-      if (devices[i] == devices[j]) return TWOACE_E_INVALID;
+  // (a device may be listed more than once: it then runs that many independent pipelines, whose kernels interleave)
   twoace_ctx* c = nullptr;
   int rc = twoace_create(devices[0], &c);
   if (rc) return rc;

@@ -1533,7 +1533,7 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
   if (!A && !cb_rows) FAIL(TWOACE_E_INVALID, "neither dense A nor codebook rows given");
   if (mem != TWOACE_MEM_HOST && mem != TWOACE_MEM_DEVICE) FAIL(TWOACE_E_INVALID, "bad mem flag");
   if (n < 1) FAIL(TWOACE_E_INVALID, "n = %d", n);
-  if (n > 256) FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift is built for n <= 256 (n = %d)", n);
+  if (n > PL_NMAX) FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift is built for n <= %d, the reference's non-largescale range (n = %d)", PL_NMAX, n);
   twoace_pl_opts o;
   if (opts) o = *opts; else twoace_pl_default_opts(&o);
   if (o.maxIts < 1 || !(o.lambda > 0.0) || !(o.L0 > 0.0) || !(o.alpha > 0.0) || !(o.beta > 0.0) || o.restart < 1 ||
@@ -1559,6 +1559,11 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
     for (size_t i = 0; i < b_off[nb]; ++i)
       if (cb_rows[i] < 0 || cb_rows[i] >= ctx->cb_rows) FAIL(TWOACE_E_INVALID, "codebook row id %d out of range", cb_rows[i]);
   }
+  // n > 256: the iteration runs in the row space of A only (d = m), so every instance needs m <= 256 and reduce = 1
+  if (n > PL_DMAX && (!o.reduce || maxm > PL_DMAX))
+    FAIL(TWOACE_E_UNSUPPORTED, "PhaseLift with n = %d > %d runs in the row space of A: needs reduce = 1 and m <= %d (m = %d)",
+         n, PL_DMAX, PL_DMAX, maxm);
+  const int dcap = pl_dcap(n, maxm);
   Staging st;
   const void *dA = nullptr, *dY = nullptr;
   void *dSig = nullptr, *dInfo = nullptr;
@@ -1576,7 +1581,7 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
   if (per_sm < 1) FAIL(TWOACE_E_CUDA, "PhaseLift kernel does not fit on an SM");
   // longest solves first is not knowable up front; instances are handed out dynamically through a counter
   const int grid = std::min(nb, per_sm * ctx->num_sms);
-  const size_t ws_stride = (pl_ws_elems(n, maxm) + 15) / 16 * 16;
+  const size_t ws_stride = (pl_ws_elems(dcap, maxm) + 15) / 16 * 16;
   Bump bp;
   const size_t o_ws = bp.take((size_t)grid * ws_stride * sizeof(cd));
   const size_t o_rows = bp.take(b_off[nb] * sizeof(int32_t));
@@ -1620,7 +1625,14 @@ static int phaselift_single(twoace_ctx* ctx, int mem, int nb, int n, const int32
   }
   rc = host_back(ctx, mem, sig, dSig, (size_t)nb * n * sizeof(cd)); if (rc) return rc;
   rc = host_back(ctx, mem, info, dInfo, (size_t)nb * PL_INFO * sizeof(double)); if (rc) return rc;
-  if (mem == TWOACE_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  if (mem == TWOACE_MEM_HOST) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n > dcap && info)
+      for (int b = 0; b < nb; ++b)
+        if (info[(size_t)b * PL_INFO + 3] == -2.0)
+          FAIL(TWOACE_E_UNSUPPORTED, "instance %d: linearly dependent measurement rows at n = %d > %d (no row-space factor)",
+               b, n, PL_DMAX);
+  }
   return TWOACE_OK;
 }
 

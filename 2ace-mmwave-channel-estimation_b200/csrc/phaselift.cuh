@@ -164,20 +164,25 @@ __device__ inline PlSmem pl_carve(unsigned char* p, int n, int maxm) {
   return s;
 }
 
-// per-CTA global workspace (cd elements): At [maxm x n], X[2], Z[2], W, U[2] (n x n each), T [max(maxm,n) x n]
-__host__ __device__ inline size_t pl_ws_elems(int n, int maxm) {
-  const size_t nn = (size_t)n * n;
-  return (size_t)maxm * n + 7 * nn + (size_t)(maxm > n ? maxm : n) * n;
+// per-CTA global workspace (cd elements): At [maxm x dcap], X[2], Z[2], W, U[2] (dcap x dcap each),
+// T [max(maxm,dcap) x dcap].  dcap = the largest dimension the iteration can run in: n for n <= PL_DMAX; for wider
+// problems the iteration only runs in the row space of A (m <= PL_DMAX rows) and dcap = maxm.
+constexpr int PL_DMAX = 256;     // block Jacobi: 16 blocks of 16
+constexpr int PL_NMAX = 2000;    // MyPhaseLift.m:87-89 switches to opts.largescale above this
+__host__ __device__ inline int pl_dcap(int n, int maxm) { return n <= PL_DMAX ? n : (maxm < PL_DMAX ? maxm : PL_DMAX); }
+__host__ __device__ inline size_t pl_ws_elems(int dcap, int maxm) {
+  const size_t nn = (size_t)dcap * dcap;
+  return (size_t)maxm * dcap + 7 * nn + (size_t)(maxm > dcap ? maxm : dcap) * dcap;
 }
 
 struct PlWs {
   cd *At, *X[2], *Z[2], *W, *U[2], *T;
 };
 
-__device__ inline PlWs pl_ws(cd* base, int n, int maxm) {
+__device__ inline PlWs pl_ws(cd* base, int dcap, int maxm) {
   PlWs w;
-  const size_t nn = (size_t)n * n;
-  w.At = base; base += (size_t)maxm * n;
+  const size_t nn = (size_t)dcap * dcap;
+  w.At = base; base += (size_t)maxm * dcap;
   w.X[0] = base; base += nn;
   w.X[1] = base; base += nn;
   w.Z[0] = base; base += nn;
@@ -250,7 +255,8 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
   const int tid = threadIdx.x;
   const int m = tk.m;
   PlSmem sm = pl_carve(smraw, n, maxm);
-  PlWs ws = pl_ws(wsbase, n, maxm);
+  const int dcap = pl_dcap(n, maxm);
+  PlWs ws = pl_ws(wsbase, dcap, maxm);
   auto Aget = [&](int i, int k) -> cd {
     if (tk.A_cm) return tk.A_cm[i + (size_t)m * k];
     return cscale(tk.cb[(size_t)tk.rows[i] * n + k], tk.scale);
@@ -307,6 +313,16 @@ __device__ inline void run_phaselift(const PlTask& tk, int n, int maxm, const Pl
       }
     }
     __syncthreads();
+  }
+  if (!reduced && n > dcap) {
+    // n > PL_DMAX and no row-space factor (rank-deficient rows): the n x n iteration is outside this kernel
+    for (int k = tid; k < n; k += NT) tk.sig[k] = cmk(NAN, NAN);
+    if (tk.info && tid == 0) {
+      for (int q = 0; q < PL_INFO; ++q) tk.info[q] = 0.0;
+      tk.info[3] = -2.0; tk.info[6] = n;
+    }
+    __syncthreads();
+    return;
   }
   if (!reduced) {
     for (size_t e = tid; e < (size_t)m * n; e += NT) ws.At[e] = Aget((int)(e % m), (int)(e / m));

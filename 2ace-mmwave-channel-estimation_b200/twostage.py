@@ -69,8 +69,7 @@ def my_two_stage_recovery(measurements, measurementMat_Input, s: int, *, opts: "
     """[recoveredSig_PLOMP, recoveredSig_PLGAMP] = My_TwoStage_Recovery(measurements, measurementMat_Input, s, ...).
     `measurements` are intensities."""
     P, Cm, mcs = svd_reduction(measurementMat_Input, s)
-    if mcs > 256:
-        raise _lib.TwoaceError(f"stage-I PhaseLift dimension mCS = {mcs} > 256 is outside this build")
+    # (mCS > 256 runs in the row space of P and needs at most 256 measurements: twoace_phaselift_batch raises otherwise)
     sig, info = _sv.phaselift_batch([P], [np.asarray(measurements, dtype=np.float64).reshape(-1)], opts, ctx)   # :115-129
     int_soln = sig[0]
     plomp = omp(Cm, int_soln, 1e-12)                                                                            # :133

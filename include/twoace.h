@@ -181,14 +181,17 @@ void twoace_pl_default_opts(twoace_pl_opts* o);
 
 #define TWOACE_PL_INFO_WORDS 16
 /* info[b*16 + k]: 0 TFOCS iterations, 1 prox_trace evaluations (= eigendecompositions), 2 backtracking steps,
- * 3 status (1 step-size tolerance, 2 iteration limit, 3 ||dx|| = 0, 4 NaN, 5 small step), 4 rank of the last
+ * 3 status (1 step-size tolerance, 2 iteration limit, 3 ||dx|| = 0, 4 NaN, 5 small step, -2 not run), 4 rank of the last
  * prox output, 5 final Lipschitz estimate L, 6 dimension iterated in (m if reduced, else n), 7 lambda_max,
  * 8 Jacobi sweeps over all eigendecompositions, 9..13 device clock cycles: gradient GEMM, warm-start transform,
  * Jacobi, z and A(z), x update and tests; 14..15 reserved. */
 
 /* Batch of independent PhaseLift solves, ragged in m.  Sensing matrices: dense `A` (concatenated m_b x n
  * column-major blocks) or, with A == NULL, rows `cb_rows` of the registered codebook scaled by `row_scale`.
- * sig: nb x n complex out.  n <= 256. */
+ * sig: nb x n complex out.  n <= 256 with any m <= 4096; 256 < n <= 2000 (up to the 32 x 32 array and beyond, the
+ * range below the reference's opts.largescale switch, MyPhaseLift.m:87-89) with reduce = 1 and every m <= 256: the
+ * iteration then runs in the m-dimensional row space of A.  Linearly dependent rows have no row-space factor; at
+ * n > 256 such an instance gets status -2 and a NaN signal, and a TWOACE_MEM_HOST call returns TWOACE_E_UNSUPPORTED. */
 int twoace_phaselift_batch(twoace_ctx* ctx, int mem, int nb, int n, const int32_t* m, const double* A,
                            const int32_t* cb_rows, double row_scale, const double* y,
                            const twoace_pl_opts* opts, double* sig, double* info);

@@ -142,6 +142,40 @@ def test_rank_deficient_rows_fall_back_to_full_dimension(gpu_ctx):
     _check_counts(tr, info)
 
 
+@pytest.mark.parametrize("shape,its", [((48, 300), 1), ((48, 300), 5), ((48, 300), 30), ((200, 640), 12),
+                                       ((120, 1024), 3)])
+def test_wide_problem_runs_in_the_row_space(gpu_ctx, shape, its):
+    """n > 256 (up to the 32x32 array, n = 1024): the GPU iterates in the m-dimensional row space of A, the oracle on
+    the full n x n matrix (initializeLinopPR.m:61-77); bounded iteration counts, same bars as the n <= 256 cases."""
+    m, n = shape
+    A, y, _ = _problem(500 + m, m, n)
+    ref, tr, sig, info = _both(A, y, gpu_ctx, maxIts=its)
+    assert sig.shape == (n,)
+    assert _err(sig, ref) < 1e-9
+    _check_counts(tr, info)
+    assert int(info[6]) == m
+
+
+def test_wide_problem_limits(gpu_ctx):
+    import twoace_b200 as tw
+    A, y, _ = _problem(77, 20, 300)
+    with pytest.raises(tw.TwoaceError, match="row space"):
+        tw.phaselift_batch([A], [y], tw.PlOpts.default(maxIts=3, reduce=0), gpu_ctx)
+    A2, y2, _ = _problem(78, 257, 300)
+    with pytest.raises(tw.TwoaceError, match="row space"):
+        tw.phaselift_batch([A2], [y2], tw.PlOpts.default(maxIts=3), gpu_ctx)
+    Ad = np.vstack([A, A[:2]])                  # dependent rows: no Cholesky factor, and d = n = 300 is not built
+    with pytest.raises(tw.TwoaceError, match="linearly dependent"):
+        tw.phaselift_batch([Ad], [np.concatenate([y, y[:2]])], tw.PlOpts.default(maxIts=3), gpu_ctx)
+    # a ragged wide batch equals the single solves bitwise
+    probs = [_problem(300 + i, mm, 400) for i, mm in enumerate([12, 90, 33])]
+    o = tw.PlOpts.default(maxIts=10)
+    sig_b, info_b = tw.phaselift_batch([q[0] for q in probs], [q[1] for q in probs], o, gpu_ctx)
+    for i, q in enumerate(probs):
+        s1, i1 = tw.phaselift_batch([q[0]], [q[1]], o, gpu_ctx)
+        assert np.array_equal(s1[0], sig_b[i]) and np.array_equal(i1[0][:9], info_b[i][:9])
+
+
 def test_zero_measurements(gpu_ctx):
     A, _, _ = _problem(9, 10, 5)
     ref, tr, sig, info = _both(A, np.zeros(10), gpu_ctx, maxIts=20)
@@ -156,7 +190,7 @@ def test_matlab_signature_and_errors(gpu_ctx):
     ref = opl.my_phase_lift(y, A, opl.TfocsOpts(maxIts=10))
     assert sig.shape == (6,) and _err(sig, ref) < 1e-9
     with pytest.raises(tw.TwoaceError):
-        tw.phaselift_batch([np.zeros((4, 300), complex)], [np.zeros(4)], None, gpu_ctx)      # n > 256
+        tw.phaselift_batch([np.zeros((4, 2001), complex)], [np.zeros(4)], None, gpu_ctx)     # the largescale range
     with pytest.raises(tw.TwoaceError):
         tw.phaselift_batch([A], [y], tw.PlOpts.default(lam=0.0), gpu_ctx)
     with pytest.raises(ValueError):

@@ -26,6 +26,7 @@ struct StageDims {
   int maxm, maxr;
   int dmax;          // max over tasks of the inverse dimension (m if Woodbury else n)
   int ds;            // dimension of the shared-memory eigenproblem (tx, or max(tx, maxr) if nuclear)
+  int wpr;           // 2-bit code words per row of A (n / 16) when the launch keeps the codes of A in shared memory, else 0
   size_t ws_stride;  // workspace elements (cd) per CTA slot
 };
 
@@ -66,7 +67,8 @@ struct StageSmem {
   double* colsc;   // [SMALL_DMAX] per-column scalars
   double* sc;      // [32] broadcast scalars
   int* ifl;        // [8] broadcast ints
-  unsigned char* jtab;   // tables of jacobi_small<16> (tx == 16 only)
+  unsigned char* jtab;   // tables of jacobi_small<16> / jacobi_small_p<32>
+  uint32_t* cw;          // [maxm * (wpr + 1)] 2-bit codes of the task's rows of A (row stride padded: conflict-free)
 };
 
 __host__ __device__ inline size_t stage_big_elems(const StageDims& d) {
@@ -86,7 +88,8 @@ __host__ __device__ inline size_t stage_smem_bytes(const StageDims& d) {
   b += 16 * NW * sizeof(double);
   b += 2 * (size_t)d.ds * sizeof(double);
   b += SMALL_DMAX * sizeof(double) + 32 * sizeof(double) + 16 * sizeof(int);
-  b += JacobiTab<16>::BYTES + 16;
+  b += (d.tx == 32 ? JacobiTab<32>::BYTES : JacobiTab<16>::BYTES) + 16;
+  if (d.wpr > 0) b += (size_t)d.maxm * (d.wpr + 1) * sizeof(uint32_t) + 16;
   return b + 64;
 }
 
@@ -109,7 +112,8 @@ __device__ inline StageSmem carve_smem(unsigned char* p, const StageDims& d) {
   s.colsc = (double*)p;  p += SMALL_DMAX * sizeof(double);
   s.sc = (double*)p;     p += 32 * sizeof(double);
   s.ifl = (int*)p;       p += 16 * sizeof(int);
-  s.jtab = p;            p += JacobiTab<16>::BYTES;
+  s.jtab = p;            p += ((d.tx == 32 ? JacobiTab<32>::BYTES : JacobiTab<16>::BYTES) + 15) / 16 * 16;
+  s.cw = (uint32_t*)p;
   s.js.flag = s.ifl + 8;
   s.js.gscale = s.sc + 31;
   return s;
@@ -145,8 +149,22 @@ __device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF o
         }
         __syncthreads();
         if (act) {
-#pragma unroll 2
-          for (int q = kslice; q < ql; q += ks) {
+          // GL elements of `mat` are loaded before the first use: the loop is bound by the latency of those
+          // loads (L2 / DRAM), not by their bandwidth
+          constexpr int GL = 8;
+          int q = kslice;
+          for (; q + (GL - 1) * ks < ql; q += GL * ks) {
+            cd a[GL];
+#pragma unroll
+            for (int u = 0; u < GL; ++u) a[u] = mat(q0 + q + u * ks, o);
+#pragma unroll
+            for (int u = 0; u < GL; ++u) {
+              const cd* tr = tile + (q + u * ks) * RCH;
+#pragma unroll
+              for (int j = 0; j < RCH; ++j) cfma(acc[j], a[u], tr[j]);
+            }
+          }
+          for (; q < ql; q += ks) {
             const cd a = mat(q0 + q, o);
             const cd* tr = tile + q * RCH;
 #pragma unroll
@@ -249,43 +267,41 @@ __device__ inline void argmin_z_v4(const StageTask& tk, const StageDims& dm, con
   // ---- eigen-decomposition.  tx == 16: warm start from the previous eigenvectors (kept in sm.U), exact
   // Schur-Horn screen (if the constraints of :449-459 already hold for the sorted diagonal of U'GU they hold
   // for the spectrum, no stage fires and Z = Z_in without any eigen-decomposition), element-form Jacobi.
-  const bool small16 = (tx == 16);
-  const bool warm = small16 && !init_mode && (sm.ifl[2] & 63) != 0;
+  const bool small16 = (tx == 16), small32 = (tx == 32);
+  const bool warm = (small16 || small32) && !init_mode && (sm.ifl[2] & 63) != 0;
   bool need_eig = true;
   if (warm) {
-    {
-      const int i = tid & 15, j = tid >> 4;
+    // G <- U' G U (Hermitian result built from its lower triangle)
+    const int tt = tx * tx;
+    for (int idx = tid; idx < tt; idx += NT) {
+      const int i = idx % tx, j = idx / tx;
       cd t0 = cmk(0.0, 0.0), t1 = t0;
-      for (int k = 0; k < 16; k += 2) {
-        cfma(t0, sm.G[i + 16 * k], sm.U[k + 16 * j]);
-        cfma(t1, sm.G[i + 16 * (k + 1)], sm.U[(k + 1) + 16 * j]);
+      for (int k = 0; k < tx; k += 2) {
+        cfma(t0, sm.G[i + tx * k], sm.U[k + tx * j]);
+        cfma(t1, sm.G[i + tx * (k + 1)], sm.U[(k + 1) + tx * j]);
       }
-      sm.P[tid] = cmk(t0.x + t1.x, t0.y + t1.y);
+      sm.P[idx] = cmk(t0.x + t1.x, t0.y + t1.y);
     }
     __syncthreads();
-    {
-      const int i = tid & 15, j = tid >> 4;
-      cd t = cmk(0.0, 0.0);
+    for (int idx = tid; idx < tt; idx += NT) {
+      const int i = idx % tx, j = idx / tx;
       if (i >= j) {
-        cd t0 = t, t1 = t;
-        for (int k = 0; k < 16; k += 2) {
-          cfmac(t0, sm.U[k + 16 * i], sm.P[k + 16 * j]);
-          cfmac(t1, sm.U[(k + 1) + 16 * i], sm.P[(k + 1) + 16 * j]);
+        cd t0 = cmk(0.0, 0.0), t1 = t0;
+        for (int k = 0; k < tx; k += 2) {
+          cfmac(t0, sm.U[k + tx * i], sm.P[k + tx * j]);
+          cfmac(t1, sm.U[(k + 1) + tx * i], sm.P[(k + 1) + tx * j]);
         }
-        t = cmk(t0.x + t1.x, t0.y + t1.y);
+        cd t = cmk(t0.x + t1.x, t0.y + t1.y);
         if (i == j) t.y = 0.0;
-      }
-      __syncthreads();
-      if (i >= j) {
-        sm.G[i + 16 * j] = t;
-        if (i != j) sm.G[j + 16 * i] = cmk(t.x, -t.y);
+        sm.G[i + tx * j] = t;
+        if (i != j) sm.G[j + tx * i] = cmk(t.x, -t.y);
       }
     }
     __syncthreads();
     if (tid == 0) {
-      double dg[16], pre = 0.0, tot = 0.0;
-      for (int i = 0; i < 16; ++i) { dg[i] = fmax(0.0, sm.G[17 * i].x); tot += dg[i]; }
-      for (int i = 1; i < 16; ++i) {   // descending insertion sort
+      double dg[SMALL_DMAX], pre = 0.0, tot = 0.0;
+      for (int i = 0; i < tx; ++i) { dg[i] = fmax(0.0, sm.G[(tx + 1) * i].x); tot += dg[i]; }
+      for (int i = 1; i < tx; ++i) {   // descending insertion sort
         const double v = dg[i]; int j = i - 1;
         while (j >= 0 && dg[j] < v) { dg[j + 1] = dg[j]; --j; }
         dg[j + 1] = v;
@@ -294,7 +310,7 @@ __device__ inline void argmin_z_v4(const StageTask& tk, const StageDims& dm, con
       const int ns = rank_profile_dev(tx, dm.rx, tk.m, n, rank_one, rl, fl);
       int ok = 1, done = 0;
       for (int k = 0; k < ns; ++k) {
-        for (; done < rl[k] && done < 16; ++done) pre += dg[done];
+        for (; done < rl[k] && done < tx; ++done) pre += dg[done];
         ok &= (pre >= tot * fl[k] * (1.0 + 1e-12)) ? 1 : 0;
       }
       sm.ifl[1] = ok;
@@ -305,9 +321,12 @@ __device__ inline void argmin_z_v4(const StageTask& tk, const StageDims& dm, con
   if (!need_eig) {
     if (tid == 0) sm.ifl[0] = 0;
   } else {
+  const long long te0 = clock64();
   int sw = small16 ? jacobi_small<16>(sm.G, sm.P, sm.U, sm.jtab, !warm)
+         : small32 ? jacobi_small_p<32>(sm.G, sm.P, sm.U, sm.jtab, !warm)
                    : jacobi_heig(sm.G, tx, sm.U, tx, tx, true, sm.js);
   if (tid == 0) {
+    sm.sc[30] += (double)(clock64() - te0);     // cycles in the eigensolver (reported in scal[9])
     sm.ifl[2] += 1;
     *sweeps_acc += sw;
     // eigenvalues, clamped (:408); stable descending order (:409)
@@ -524,6 +543,10 @@ __device__ inline void argmin_z_nuclear(const StageTask& tk, const StageDims& dm
 }
 
 // ------------------------------------------------------------------------------------------
+// CM: A = (*tk.cscale) * u(code) with the 2-bit codes of the task's rows held in shared memory: the products of the
+// iteration read no A from global memory (for n = 1024 the dense A of one instance is 3 MB, of a batch far more than
+// L2, and the dense loop is bound by the latency of those loads).  The set-up (S and its inverse) still reads dense A.
+template <bool CM>
 __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, const StageDims& dm,
                                  const StageWS& ws, const StageSmem& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -531,7 +554,9 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   const bool wood = use_woodbury(m, n);
   const int dS = wood ? m : n;
   const cd* Ab = tk.A.base;
-  const double asc = *tk.A.scale;
+  const double asc_dense = *tk.A.scale;
+  const double asc = CM ? *tk.cscale : asc_dense;      // scale applied to the A' products
+  const int cws = dm.wpr + 1;
   const size_t nr = (size_t)n * r, mr = (size_t)m * r;
 
   // ---- stage-local copies: row ids, B, column-major A
@@ -545,7 +570,13 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {
     const int k = (int)(idx % n), i = (int)(idx / n);
     cd a = Ab[(size_t)sm.rows_s[i] * n + k];
-    ws.Acm[i + (size_t)m * k] = cmk(a.x * asc, a.y * asc);
+    ws.Acm[i + (size_t)m * k] = cmk(a.x * asc_dense, a.y * asc_dense);
+  }
+  if constexpr (CM) {
+    for (int idx = tid; idx < m * dm.wpr; idx += NT) {
+      const int i = idx / dm.wpr, w = idx - i * dm.wpr;
+      sm.cw[i * cws + w] = tk.codes[(size_t)sm.rows_s[i] * dm.wpr + w];
+    }
   }
   double nb2;
   {
@@ -555,6 +586,10 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
     nb2 = v[0];
   }
   const double normB = sqrt(nb2);
+  // device cycle counters of the phases (thread 0; scal[9..14], the layout of the cluster kernels)
+  long long cyc_x = 0, cyc_y = 0, cyc_z = 0, cyc_loop = 0;
+  const long long t_begin = clock64();
+  if (tid == 0) sm.sc[30] = 0.0;
 
   // ---- S = I + A A' (Woodbury) or A'A + I, then its inverse (inferLowRankV4.m:221 / :267)
   if (wood) {
@@ -573,7 +608,7 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
       else if (i == j) ws.Sinv[idx].y = 0.0;
     }
   } else {
-    const double as2 = asc * asc;
+    const double as2 = asc_dense * asc_dense;
     for (size_t idx = tid; idx < (size_t)n * n; idx += NT) {
       const int k = (int)(idx % n), l = (int)(idx / n);
       cd acc = cmk(0.0, 0.0);
@@ -592,10 +627,25 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   for (size_t idx = tid; idx < mr; idx += NT) ws.M[idx] = cmk(0.0, 0.0);
   __syncthreads();
 
-  auto matA = [&](int k, int i) -> cd { return ws.Acm[i + (size_t)m * k]; };             // A(i,k), out=i
+  auto ucode = [&](int i, int k) -> unsigned { return (sm.cw[i * cws + (k >> 4)] >> (2 * (k & 15))) & 3u; };
+  auto matA = [&](int k, int i) -> cd {                                                  // A(i,k), out=i
+    if constexpr (CM) {
+      const unsigned c = ucode(i, k);
+      const double v = (c & 2u) ? -asc : asc;
+      return (c & 1u) ? cmk(0.0, v) : cmk(v, 0.0);
+    } else {
+      return ws.Acm[i + (size_t)m * k];
+    }
+  };
   auto matAh = [&](int i, int k) -> cd {                                                 // conj(A(i,k))/scale, out=k
-    cd a = Ab[(size_t)sm.rows_s[i] * n + k];
-    return cmk(a.x, -a.y);
+    if constexpr (CM) {
+      const unsigned c = ucode(i, k);
+      const double v = (c & 2u) ? -1.0 : 1.0;
+      return (c & 1u) ? cmk(0.0, -v) : cmk(v, 0.0);
+    } else {
+      cd a = Ab[(size_t)sm.rows_s[i] * n + k];
+      return cmk(a.x, -a.y);
+    }
   };
 
   // AX = A * X                                                                   (:278)
@@ -650,6 +700,7 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   double nz[4];
   if (tid == 0) sm.ifl[2] = 0;
   if (dm.tx == 16) jacobi_tables<16>(sm.jtab);
+  else if (dm.tx == 32) jacobi_tables<32>(sm.jtab);
   __syncthreads();
   // Z = ArgMinZ(X, N=0, mu=1)                                                    (:288)
   if (tk.nuclear) argmin_z_nuclear(tk, dm, ws, sm, 1.0, true, nz, &sweeps);
@@ -664,9 +715,11 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
 
   double mu = prm.mu0, opt_obj = INFINITY, last_res = INFINITY, res_comb = 0.0;
   int iters = 0, opt_iter = -1, opt_col = -1, bumps = 0, converged = 0, have_opt = 0;
+  const long long t_loop = clock64();
 
   for (int it = 1; it <= prm.maxiter; ++it) {
     const double imu = 1.0 / mu;
+    const long long t0 = clock64();
     // ---- X update (:304, :380-388):  X = inv(A'A+I) (A'T + Q),  T = Y - M/mu,  Q = Z - N/mu
     if (wood) {
       // two-product Woodbury form:  X = Q + A' W,  A X = T - W,  W = S^-1 (T - A Q),  S = I + A A'
@@ -716,6 +769,8 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
                [&](int i, int c, cd v) { ws.AX[i + (size_t)m * c] = v; }, sm.tile, sm.big);
     }
     // ---- Y update (:308, :490-512), M update (:315-316), objective (:323-340), Y/AX norms
+    const long long t1 = clock64();
+    cyc_x += t1 - t0;
     double nYd2 = 0.0, nJM2 = 0.0, nAX2 = 0.0, nY2 = 0.0, obj2 = 0.0;
     const double i1mu = 1.0 / (1.0 + mu);
     if (tk.sbr) {
@@ -795,8 +850,11 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
       nAtYd2 = v[0]; nAtY2 = v[1];
     }
     // ---- Z update (:312), N update (:319-320), X/Z norms
+    const long long t2 = clock64();
+    cyc_y += t2 - t1;
     if (tk.nuclear) argmin_z_nuclear(tk, dm, ws, sm, mu, false, nz, &sweeps);
     else argmin_z_v4(tk, dm, ws, sm, mu, false, rank_one, nz, &sweeps);
+    cyc_z += clock64() - t2;
     const double nJN2 = nz[0], nZd2 = nz[1], nX2 = nz[2], nZ2 = nz[3];
 
     // ---- best solution so far (:323-340).  NaN objectives never win (MATLAB min skips NaN).
@@ -840,6 +898,7 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
     __syncthreads();
   }
   __syncthreads();
+  cyc_loop = clock64() - t_loop;
   // ---- outputs (:363-364)
   const int rout = tk.sbr ? r : 1;
   for (size_t idx = tid; idx < (size_t)n * rout; idx += NT)
@@ -855,6 +914,8 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
     tk.scal[SC_MU] = mu; tk.scal[SC_OPT_OBJ] = opt_obj; tk.scal[SC_ITERS] = iters;
     tk.scal[SC_OPT_ITER] = opt_iter; tk.scal[SC_OPT_COL] = opt_col; tk.scal[SC_BUMPS] = bumps;
     tk.scal[SC_CONVERGED] = converged; tk.scal[SC_RES_COMB] = res_comb; tk.scal[SC_SWEEPS] = sweeps;
+    tk.scal[9] = sm.sc[30]; tk.scal[10] = (double)cyc_x; tk.scal[11] = (double)cyc_loop; tk.scal[12] = (double)cyc_y;
+    tk.scal[13] = (double)cyc_z; tk.scal[14] = (double)(t_loop - t_begin);     // [14]: set-up (S, its inverse, first Z)
   }
   __syncthreads();
 }
@@ -868,7 +929,8 @@ admm_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm
     const StageTask tk = tasks[t];
     if (tk.active != nullptr && *tk.active != tk.active_expect) continue;
     if (tk.m <= 0 || tk.r <= 0) continue;
-    run_stage(tk, prm, dm, ws, sm);
+    if (dm.wpr > 0 && tk.codes != nullptr && tk.cscale != nullptr) run_stage<true>(tk, prm, dm, ws, sm);
+    else run_stage<false>(tk, prm, dm, ws, sm);
   }
 }
 

@@ -465,6 +465,14 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
   dm.ds = nuc ? std::max(tx, dm.maxr) : tx;
   if (dm.ds > SMALL_DMAX) FAIL(TWOACE_E_UNSUPPORTED, "tx (or r for the nuclear variant) > %d", SMALL_DMAX);
   dm.ws_stride = (stage_ws_elems(dm) + 15) / 16 * 16;
+  // tasks that carry 2-bit codes of A keep them in shared memory when the rows of the largest task fit
+  dm.wpr = 0;
+  bool any_codes = false;
+  for (const StageTask& t : tasks) any_codes = any_codes || (t.codes != nullptr && t.cscale != nullptr);
+  if (any_codes && n % 16 == 0) {
+    dm.wpr = n / 16;
+    if (stage_smem_bytes(dm) > SMEM_LIMIT) dm.wpr = 0;
+  }
   const size_t smem = stage_smem_bytes(dm);
   int grid = 0;
   rc = stage_grid(ctx, smem, (int)tasks.size(), &grid);
@@ -482,7 +490,8 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
     char lb[160];
-    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d", tasks.size(), grid, dm.maxm, dm.maxr);
+    snprintf(lb, sizeof lb, "admm_stage_kernel tasks %zu grid %d maxm %d maxr %d%s", tasks.size(), grid, dm.maxm, dm.maxr,
+             dm.wpr ? " codes" : "");
     push_stage_event(ctx, e0, e1, lb);
   }
   ctx->launches++;
@@ -875,14 +884,17 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
   const size_t o_ymax = bp.take(b_off[nb] * sizeof(cd));
   const size_t o_yr = bp.take(b_off[nb] * sizeof(cd));
   const size_t o_sw = bp.take((size_t)nb * nstage * STAGE_SCAL * sizeof(double));
-  const bool try_codes = ctx->opt_fast && n == FN && in.tx == FTX && in.rx == FTX;
-  const size_t o_codes = (dense && try_codes) ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
+  // 2-bit codes of A: the cluster kernels need them (16 x 16 arrays), the general kernel keeps them in shared memory
+  const bool try_fast = ctx->opt_fast && n == FN && in.tx == FTX && in.rx == FTX;
+  const bool try_codes = ctx->opt_fast && n % 16 == 0;
+  const int wpr = n / 16;
+  const size_t o_codes = (dense && try_codes) ? bp.take(b_off[nb] * wpr * sizeof(uint32_t)) : 0;
   const size_t o_qflag = (dense && try_codes) ? bp.take((size_t)nb * sizeof(int)) : 0;
   // per-instance store of (I + A_train A_train')^-1: the stages of a trial (over-parameterised, refinement and their
   // rank-one reruns) share the training rows, so only the first of them inverts (instances on the cluster kernels;
   // m x m Woodbury core for m <= 256, the n x n matrix (A'A + I)^-1 of the chunked kernel above)
   std::vector<size_t> sv_off(nb + 1, 0);
-  for (int b = 0; b < nb; ++b) sv_off[b + 1] = sv_off[b] + ((try_codes && ctx->opt_cache_sinv && mtr[b] <= BIG_MMAX) ? (mtr[b] <= 256 ? (size_t)mtr[b] * mtr[b] : (size_t)FN * FN) : 0);
+  for (int b = 0; b < nb; ++b) sv_off[b + 1] = sv_off[b] + ((try_fast && ctx->opt_cache_sinv && mtr[b] <= BIG_MMAX) ? (mtr[b] <= 256 ? (size_t)mtr[b] * mtr[b] : (size_t)FN * FN) : 0);
   const size_t o_sinv = sv_off[nb] ? bp.take(sv_off[nb] * sizeof(cd)) : 0;
   int rc = ensure(ctx, ctx->arena, bp.off + 256);
   if (rc) return rc;
@@ -938,7 +950,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       std::vector<QuantTask> qt(nb);
       for (int b = 0; b < nb; ++b) {
         QuantTask& q = qt[b];
-        q.A_rm = d_Arm + a_off[b]; q.rows = in.m[b]; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * 16;
+        q.A_rm = d_Arm + a_off[b]; q.rows = in.m[b]; q.wpr = wpr; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * wpr;
         q.mag_out = nullptr; q.flag_out = (int*)(base + o_qflag) + b; q.ctl = d_ctl + b;
       }
       const QuantTask* dq = nullptr;
@@ -999,7 +1011,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
         a.scal = d_sw + ((size_t)b * nstage + 4 * t + 2 * pass) * STAGE_SCAL; a.state = nullptr;
         a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + 4 * t + 2 * pass) * in.p.maxiter : nullptr;
         const bool use_codes = inst_codes[b] != 0;
-        a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
+        a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * wpr : ctx->cb_codes);
         a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
         if (use_codes && sv_off[b + 1] > sv_off[b]) { a.sinv = (cd*)(base + o_sinv) + sv_off[b]; a.sinv_state = pass ? 1 : 0; }
         StageTask& s2 = sb[b];
@@ -1053,7 +1065,7 @@ static int solve_chunk(twoace_ctx* ctx, const ChunkIn& in) {
       a.scal = d_sw + ((size_t)b * nstage + (nstage - 1)) * STAGE_SCAL; a.state = nullptr;
       a.trace = in.dTrace ? in.dTrace + ((size_t)b * nstage + (nstage - 1)) * in.p.maxiter : nullptr;
       const bool use_codes = inst_codes[b] != 0;
-      a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : ctx->cb_codes);
+      a.codes = !use_codes ? nullptr : (dense ? (const uint32_t*)(base + o_codes) + b_off[b] * wpr : ctx->cb_codes);
       a.cscale = use_codes ? &d_ctl[b].c_scale : nullptr;
       FinalTask& f = ft[b];
       f.x0 = d_xmax + (size_t)b * n; f.y0 = d_ymax + b_off[b]; f.xr = d_xr + (size_t)b * n; f.yr = d_yr + b_off[b];
@@ -1316,13 +1328,13 @@ extern "C" int twoace_set_codebook(twoace_ctx* ctx, int mem, int rows, int n, co
   ctx->cb_rows = rows; ctx->cb_n = n;
   if (ctx->cb_codes) { CK(cudaFree(ctx->cb_codes)); ctx->cb_codes = nullptr; }
   ctx->cb_mag = 0.0;
-  if (n == FN) {   // try the 2-bit representation (every shipped codebook qualifies)
+  if (n % 16 == 0) {   // try the 2-bit representation (every shipped codebook qualifies)
     uint32_t* codes = nullptr;
-    CK(cudaMalloc((void**)&codes, (size_t)rows * 16 * sizeof(uint32_t) + 64));
+    CK(cudaMalloc((void**)&codes, (size_t)rows * (n / 16) * sizeof(uint32_t) + 64));
     char* aux = nullptr;
     CK(cudaMalloc((void**)&aux, 64 + sizeof(QuantTask)));
     QuantTask q;
-    q.A_rm = ctx->cb_rm; q.rows = rows; q.codes = codes; q.mag_out = (double*)aux; q.flag_out = (int*)(aux + 8); q.ctl = nullptr;
+    q.A_rm = ctx->cb_rm; q.rows = rows; q.wpr = n / 16; q.codes = codes; q.mag_out = (double*)aux; q.flag_out = (int*)(aux + 8); q.ctl = nullptr;
     CK(cudaMemcpyAsync(aux + 64, &q, sizeof q, cudaMemcpyHostToDevice, ctx->stream));
     quant_kernel<<<1, NT, 0, ctx->stream>>>((const QuantTask*)(aux + 64), 1);
     CK(cudaGetLastError());
@@ -1384,8 +1396,9 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
   Bump bp;
   const size_t o_Arm = bp.take(a_off[nb] * sizeof(cd)), o_one = bp.take(sizeof(double));
   const size_t o_ctl = bp.take((size_t)nb * sizeof(InstCtl));
-  const bool try_codes = ctx->opt_fast && n == FN && tx == FTX && rx == FTX && (r == 20 || r == 1);
-  const size_t o_codes = try_codes ? bp.take(b_off[nb] * 16 * sizeof(uint32_t)) : 0;
+  const bool try_codes = ctx->opt_fast && n % 16 == 0;
+  const int wpr = n / 16;
+  const size_t o_codes = try_codes ? bp.take(b_off[nb] * wpr * sizeof(uint32_t)) : 0;
   const size_t o_qflag = try_codes ? bp.take((size_t)nb * sizeof(int)) : 0;
   const size_t o_mag = try_codes ? bp.take((size_t)nb * sizeof(double)) : 0;
   rc = ensure(ctx, ctx->arena, bp.off + 256); if (rc) return rc;
@@ -1417,7 +1430,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
     std::vector<QuantTask> qt(nb);
     for (int b = 0; b < nb; ++b) {
       QuantTask& q = qt[b];
-      q.A_rm = d_Arm + a_off[b]; q.rows = m[b]; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * 16;
+      q.A_rm = d_Arm + a_off[b]; q.rows = m[b]; q.wpr = wpr; q.codes = (uint32_t*)(base + o_codes) + b_off[b] * wpr;
       q.mag_out = (double*)(base + o_mag) + b; q.flag_out = (int*)(base + o_qflag) + b; q.ctl = nullptr;
     }
     const QuantTask* dq = nullptr;
@@ -1434,7 +1447,7 @@ extern "C" int twoace_infer_admm_batch(twoace_ctx* ctx, int mem, int nb, int tx,
   for (int b = 0; b < nb; ++b) {
     StageTask& a = tasks[b];
     const bool use_codes = inst_codes[b] != 0;
-    a.codes = use_codes ? (const uint32_t*)(base + o_codes) + b_off[b] * 16 : nullptr;
+    a.codes = use_codes ? (const uint32_t*)(base + o_codes) + b_off[b] * wpr : nullptr;
     a.cscale = use_codes ? (const double*)(base + o_mag) + b : nullptr;
     a.A.base = d_Arm + a_off[b]; a.A.rows = nullptr; a.A.scale = d_one;
     a.B = (const double*)dB + b_off[b]; a.brows = nullptr; a.bscale = d_one;

@@ -486,11 +486,12 @@ __global__ void __launch_bounds__(NT) final_kernel(const FinalTask* __restrict__
 // ---- 2-bit phase-code extraction -----------------------------------------------------------------
 // A row-major matrix whose entries are all c * {1, j, -1, -j} (one common magnitude c, residues below
 // 1e-15 c tolerated: the shipped .mat codebooks carry cos(pi/2) = 6e-17) is re-expressed as 2-bit codes,
-// 16 per 32-bit word, 16 words per row (n = 256).  One CTA per matrix.
+// 16 per 32-bit word, wpr = n / 16 words per row (16 for n = 256).  One CTA per matrix.
 struct QuantTask {
-  const cd* A_rm;      // rows x 256 row-major
+  const cd* A_rm;      // rows x n row-major
   int rows;
-  uint32_t* codes;     // rows x 16 words
+  int wpr;             // words per row (n / 16)
+  uint32_t* codes;     // rows x wpr words
   double* mag_out;     // c (may be nullptr)
   int* flag_out;       // 1 = quantised
   InstCtl* ctl;        // optional: sets ctl->quant and ctl->c_scale = a_scale * c
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(NT) quant_kernel(const QuantTask* __restrict__
     const double c = fmax(fabs(a0.x), fabs(a0.y));
     const double tol = 1e-15 * c;
     int bad = (c > 0.0) ? 0 : 1;
-    for (size_t w = tid; w < (size_t)tk.rows * 16; w += NT) {
+    for (size_t w = tid; w < (size_t)tk.rows * tk.wpr; w += NT) {
       const cd* a = tk.A_rm + w * 16;
       uint32_t word = 0;
       for (int j = 0; j < 16; ++j) {

@@ -124,28 +124,28 @@ __device__ inline StageSmem carve_smem(unsigned char* p, const StageDims& d) {
 // One thread per output row o holds RCH column accumulators; opnd is staged in shared tiles of
 // QT x RCH; mat(q, o) must be coalesced over o.  When nout is small the reduction is split over
 // up to 8 thread groups and the partials are combined through `ksred`.
-template <class MatF, class OpF, class StoreF>
-__device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF opnd, StoreF store,
+template <int RC, class MatF, class OpF, class StoreF>
+__device__ __forceinline__ void gemm_tpo_t(int nout, int K, int r, MatF mat, OpF opnd, StoreF store,
                                          cd* tile, cd* ksred) {
   const int tid = threadIdx.x;
   int ks = 1;
   while (ks < 8 && 2 * ks * nout <= NT) ks *= 2;
   const int OB = (ks == 1) ? NT : nout;   // outputs per pass
   const int o_in = tid % OB, kslice = tid / OB;
-  for (int c0 = 0; c0 < r; c0 += RCH) {
-    const int rc = min(RCH, r - c0);
+  for (int c0 = 0; c0 < r; c0 += RC) {
+    const int rc = min(RC, r - c0);
     for (int ob = 0; ob < nout; ob += OB) {
       const int o = ob + o_in;
       const bool act = (o < nout) && (kslice < ks);
-      cd acc[RCH];
+      cd acc[RC];
 #pragma unroll
-      for (int j = 0; j < RCH; ++j) acc[j] = cmk(0.0, 0.0);
+      for (int j = 0; j < RC; ++j) acc[j] = cmk(0.0, 0.0);
       for (int q0 = 0; q0 < K; q0 += QT) {
         const int ql = min(QT, K - q0);
         __syncthreads();
-        for (int idx = tid; idx < QT * RCH; idx += NT) {
+        for (int idx = tid; idx < QT * RC; idx += NT) {
           int j = idx / QT, q = idx - j * QT;   // q fastest: coalesced operand reads
-          tile[q * RCH + j] = (q < ql && j < rc) ? opnd(q0 + q, c0 + j) : cmk(0.0, 0.0);
+          tile[q * RC + j] = (q < ql && j < rc) ? opnd(q0 + q, c0 + j) : cmk(0.0, 0.0);
         }
         __syncthreads();
         if (act) {
@@ -159,16 +159,16 @@ __device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF o
             for (int u = 0; u < GL; ++u) a[u] = mat(q0 + q + u * ks, o);
 #pragma unroll
             for (int u = 0; u < GL; ++u) {
-              const cd* tr = tile + (q + u * ks) * RCH;
+              const cd* tr = tile + (q + u * ks) * RC;
 #pragma unroll
-              for (int j = 0; j < RCH; ++j) cfma(acc[j], a[u], tr[j]);
+              for (int j = 0; j < RC; ++j) cfma(acc[j], a[u], tr[j]);
             }
           }
           for (; q < ql; q += ks) {
             const cd a = mat(q0 + q, o);
-            const cd* tr = tile + q * RCH;
+            const cd* tr = tile + q * RC;
 #pragma unroll
-            for (int j = 0; j < RCH; ++j) cfma(acc[j], a, tr[j]);
+            for (int j = 0; j < RC; ++j) cfma(acc[j], a, tr[j]);
           }
         }
       }
@@ -176,14 +176,14 @@ __device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF o
         __syncthreads();
         if (act) {
 #pragma unroll
-          for (int j = 0; j < RCH; ++j) ksred[((size_t)kslice * nout + o) * RCH + j] = acc[j];
+          for (int j = 0; j < RC; ++j) ksred[((size_t)kslice * nout + o) * RC + j] = acc[j];
         }
         __syncthreads();
         if (act && kslice == 0) {
           for (int s = 1; s < ks; ++s) {
 #pragma unroll
-            for (int j = 0; j < RCH; ++j) {
-              cd v = ksred[((size_t)s * nout + o) * RCH + j];
+            for (int j = 0; j < RC; ++j) {
+              cd v = ksred[((size_t)s * nout + o) * RC + j];
               acc[j].x += v.x;
               acc[j].y += v.y;
             }
@@ -192,12 +192,20 @@ __device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF o
       }
       if (act && kslice == 0) {
 #pragma unroll
-        for (int j = 0; j < RCH; ++j)
+        for (int j = 0; j < RC; ++j)
           if (j < rc) store(o, c0 + j, acc[j]);
       }
     }
   }
   __syncthreads();
+}
+
+// r == 1 (the refinement stages) runs with one column accumulator instead of RCH.
+template <class MatF, class OpF, class StoreF>
+__device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF opnd, StoreF store,
+                                         cd* tile, cd* ksred) {
+  if (r == 1) gemm_tpo_t<1>(nout, K, r, mat, opnd, store, tile, ksred);
+  else gemm_tpo_t<RCH>(nout, K, r, mat, opnd, store, tile, ksred);
 }
 
 // Rank-shaping profile of inferLowRankV4.m:416-443.  Returns the number of (r_k, f_k) stages.
@@ -567,10 +575,12 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
     sm.Bs[i] = bsc * tk.B[tk.brows ? tk.brows[i] : i];
   }
   __syncthreads();
-  for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {
-    const int k = (int)(idx % n), i = (int)(idx / n);
-    cd a = Ab[(size_t)sm.rows_s[i] * n + k];
-    ws.Acm[i + (size_t)m * k] = cmk(a.x * asc_dense, a.y * asc_dense);
+  if constexpr (!CM) {   // (with codes nothing below reads the column-major copy)
+    for (size_t idx = tid; idx < (size_t)m * n; idx += NT) {
+      const int k = (int)(idx % n), i = (int)(idx / n);
+      cd a = Ab[(size_t)sm.rows_s[i] * n + k];
+      ws.Acm[i + (size_t)m * k] = cmk(a.x * asc_dense, a.y * asc_dense);
+    }
   }
   if constexpr (CM) {
     for (int idx = tid; idx < m * dm.wpr; idx += NT) {
@@ -593,12 +603,36 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
 
   // ---- S = I + A A' (Woodbury) or A'A + I, then its inverse (inferLowRankV4.m:221 / :267)
   if (wood) {
-    for (int idx = tid; idx < m * m; idx += NT) {
-      const int i = idx % m, j = idx / m;
-      cd acc = cmk(i == j ? 1.0 : 0.0, 0.0);
-      if (i >= j) {
-        for (int k = 0; k < n; ++k) cfmabc(acc, ws.Acm[i + (size_t)m * k], ws.Acm[j + (size_t)m * k]);
-        ws.Sinv[idx] = acc;
+    if constexpr (CM) {
+      // u_i(k) conj(u_j(k)) = j^((c_i - c_j) mod 4): the 16 differences of a word pair come from one 2-bit-field
+      // subtraction, their counts from three popcounts; the sum over k is exact integer arithmetic
+      constexpr uint32_t HB = 0xAAAAAAAAu, LB = 0x55555555u;
+      const double as2 = asc * asc;
+      for (int idx = tid; idx < m * m; idx += NT) {
+        const int i = idx % m, j = idx / m;
+        if (i >= j) {
+          const uint32_t* wi = sm.cw + i * cws;
+          const uint32_t* wj = sm.cw + j * cws;
+          int re = 0, im = 0;
+          for (int w = 0; w < dm.wpr; ++w) {
+            const uint32_t x = wi[w], y = wj[w];
+            const uint32_t d = ((x | HB) - (y & LB)) ^ ((x ^ ~y) & HB);
+            const uint32_t hi = (d >> 1) & LB, lo = d & LB;
+            const int n3 = __popc(hi & lo), n2 = __popc(hi & ~lo), n1 = __popc(lo & ~hi);
+            re += 16 - n1 - 2 * n2 - n3;     // n0 - n2
+            im += n1 - n3;
+          }
+          ws.Sinv[idx] = cmk(fma(as2, (double)re, i == j ? 1.0 : 0.0), as2 * (double)im);
+        }
+      }
+    } else {
+      for (int idx = tid; idx < m * m; idx += NT) {
+        const int i = idx % m, j = idx / m;
+        cd acc = cmk(i == j ? 1.0 : 0.0, 0.0);
+        if (i >= j) {
+          for (int k = 0; k < n; ++k) cfmabc(acc, ws.Acm[i + (size_t)m * k], ws.Acm[j + (size_t)m * k]);
+          ws.Sinv[idx] = acc;
+        }
       }
     }
     __syncthreads();

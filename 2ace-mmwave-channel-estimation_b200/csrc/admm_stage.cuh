@@ -200,11 +200,90 @@ __device__ __forceinline__ void gemm_tpo_t(int nout, int K, int r, MatF mat, OpF
   __syncthreads();
 }
 
-// r == 1 (the refinement stages) runs with one column accumulator instead of RCH.
+// Two output rows per thread (o and o + half of the pass) and RC columns: every operand read from the shared tile
+// feeds two complex FMAs.  With `mat` cheap (2-bit codes) the one-row form is bound by the throughput of those
+// warp-broadcast reads (ncu: short scoreboard 55 % of the samples in the loop).  A pass of at most NT rows splits the
+// reduction over two thread groups so that all warps stay busy.  nout > NT / 2.
+template <int RC, class MatF, class OpF, class StoreF>
+__device__ __forceinline__ void gemm_tpo_2r(int nout, int K, int r, MatF mat, OpF opnd, StoreF store, cd* tile,
+                                            cd* ksred) {
+  const int tid = threadIdx.x;
+  for (int c0 = 0; c0 < r; c0 += RC) {
+    const int rc = min(RC, r - c0);
+    for (int ob = 0; ob < nout; ob += 2 * NT) {
+      const int rows = min(2 * NT, nout - ob), half = (rows + 1) / 2;
+      const int ks = (2 * half <= NT) ? 2 : 1;
+      const int kslice = tid / half, o_in = tid - kslice * half;
+      const bool act0 = kslice < ks, act1 = act0 && (half + o_in < rows);
+      const int o0 = ob + o_in, o1 = act1 ? ob + half + o_in : o0;
+      cd acc0[RC], acc1[RC];
+#pragma unroll
+      for (int j = 0; j < RC; ++j) { acc0[j] = cmk(0.0, 0.0); acc1[j] = cmk(0.0, 0.0); }
+      for (int q0 = 0; q0 < K; q0 += QT) {
+        const int ql = min(QT, K - q0);
+        __syncthreads();
+        for (int idx = tid; idx < QT * RC; idx += NT) {
+          int j = idx / QT, q = idx - j * QT;
+          tile[q * RC + j] = (q < ql && j < rc) ? opnd(q0 + q, c0 + j) : cmk(0.0, 0.0);
+        }
+        __syncthreads();
+        if (act0) {
+          constexpr int GL = 4;
+          int q = kslice;
+          for (; q + (GL - 1) * ks < ql; q += GL * ks) {
+            cd a0[GL], a1[GL];
+#pragma unroll
+            for (int u = 0; u < GL; ++u) { a0[u] = mat(q0 + q + u * ks, o0); a1[u] = mat(q0 + q + u * ks, o1); }
+#pragma unroll
+            for (int u = 0; u < GL; ++u) {
+              const cd* tr = tile + (q + u * ks) * RC;
+#pragma unroll
+              for (int j = 0; j < RC; ++j) { const cd t = tr[j]; cfma(acc0[j], a0[u], t); cfma(acc1[j], a1[u], t); }
+            }
+          }
+          for (; q < ql; q += ks) {
+            const cd a0 = mat(q0 + q, o0), a1 = mat(q0 + q, o1);
+            const cd* tr = tile + q * RC;
+#pragma unroll
+            for (int j = 0; j < RC; ++j) { const cd t = tr[j]; cfma(acc0[j], a0, t); cfma(acc1[j], a1, t); }
+          }
+        }
+      }
+      if (ks > 1) {
+        __syncthreads();
+        if (act0 && kslice == 1) {
+#pragma unroll
+          for (int j = 0; j < RC; ++j) { ksred[(size_t)o_in * 2 * RC + j] = acc0[j]; ksred[(size_t)o_in * 2 * RC + RC + j] = acc1[j]; }
+        }
+        __syncthreads();
+        if (act0 && kslice == 0) {
+#pragma unroll
+          for (int j = 0; j < RC; ++j) {
+            const cd v0 = ksred[(size_t)o_in * 2 * RC + j], v1 = ksred[(size_t)o_in * 2 * RC + RC + j];
+            acc0[j].x += v0.x; acc0[j].y += v0.y;
+            acc1[j].x += v1.x; acc1[j].y += v1.y;
+          }
+        }
+      }
+      if (act0 && kslice == 0) {
+#pragma unroll
+        for (int j = 0; j < RC; ++j)
+          if (j < rc) {
+            store(o0, c0 + j, acc0[j]);
+            if (act1) store(o1, c0 + j, acc1[j]);
+          }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// r == 1 (the refinement stages) runs with one column accumulator instead of RCH; wide outputs with two rows per thread.
 template <class MatF, class OpF, class StoreF>
 __device__ __forceinline__ void gemm_tpo(int nout, int K, int r, MatF mat, OpF opnd, StoreF store,
                                          cd* tile, cd* ksred) {
   if (r == 1) gemm_tpo_t<1>(nout, K, r, mat, opnd, store, tile, ksred);
+  else if (nout > NT / 2) gemm_tpo_2r<RCH / 2>(nout, K, r, mat, opnd, store, tile, ksred);
   else gemm_tpo_t<RCH>(nout, K, r, mat, opnd, store, tile, ksred);
 }
 

@@ -1033,6 +1033,14 @@ __device__ inline void run_stage(const StageTask& tk, const DevParams& prm, cons
   __syncthreads();
 }
 
+// The kernel lives in its own translation unit (gen_kernel.cu; api.cu reaches it through these host functions): its two
+// instantiations of run_stage are half of the library's compile time, and the translation units build in parallel.
+cudaError_t gen_kernel_set_smem(size_t smem);
+cudaError_t gen_kernel_occupancy(int* per_sm, size_t smem);
+cudaError_t gen_kernel_launch(int grid, size_t smem, cudaStream_t stream, const StageTask* tasks, int ntasks, DevParams prm,
+                              StageDims dm, cd* wsbase);
+
+#ifdef TWOACE_GEN_KERNEL_TU
 __global__ void __launch_bounds__(NT, 2)
 admm_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm, StageDims dm, cd* wsbase) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1046,5 +1054,18 @@ admm_stage_kernel(const StageTask* __restrict__ tasks, int ntasks, DevParams prm
     else run_stage<false>(tk, prm, dm, ws, sm);
   }
 }
+
+cudaError_t gen_kernel_set_smem(size_t smem) {
+  return cudaFuncSetAttribute(admm_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+cudaError_t gen_kernel_occupancy(int* per_sm, size_t smem) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, admm_stage_kernel, NT, smem);
+}
+cudaError_t gen_kernel_launch(int grid, size_t smem, cudaStream_t stream, const StageTask* tasks, int ntasks, DevParams prm,
+                              StageDims dm, cd* wsbase) {
+  admm_stage_kernel<<<grid, NT, smem, stream>>>(tasks, ntasks, prm, dm, wsbase);
+  return cudaGetLastError();
+}
+#endif
 
 }  // namespace twoace

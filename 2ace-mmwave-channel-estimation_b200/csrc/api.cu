@@ -267,8 +267,8 @@ static int upload_tasks(twoace_ctx* ctx, const std::vector<T>& v, size_t& cursor
 
 static int stage_grid(twoace_ctx* ctx, size_t smem, int ntasks, int* grid) {
   int occ = 0;
-  CK(cudaFuncSetAttribute(admm_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, admm_stage_kernel, NT, smem));
+  CK(gen_kernel_set_smem(smem));
+  CK(gen_kernel_occupancy(&occ, smem));
   if (occ < 1) FAIL(TWOACE_E_UNSUPPORTED, "stage kernel does not fit: %zu bytes of shared memory", smem);
   *grid = std::max(1, std::min(ntasks, occ * ctx->num_sms));
   return 0;
@@ -485,8 +485,7 @@ static int launch_stage_general(twoace_ctx* ctx, const std::vector<StageTask>& t
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
   }
-  admm_stage_kernel<<<grid, NT, smem, ctx->stream>>>(dt, (int)tasks.size(), prm, dm, (cd*)ctx->ws.p);
-  CK(cudaGetLastError());
+  CK(gen_kernel_launch(grid, smem, ctx->stream, dt, (int)tasks.size(), prm, dm, (cd*)ctx->ws.p));
   if (ctx->timing) {
     CK(cudaEventRecord(e1, ctx->stream));
     char lb[160];

@@ -548,6 +548,29 @@ def test_stage_parity_other_antenna_counts(gpu_ctx, tx, rx, m, nuc):
         assert int(W[0][3]) == tro.opt_iter
 
 
+@pytest.mark.parametrize("tx,rx,m,r", [(32, 32, 200, 20), (32, 32, 200, 1), (8, 32, 70, 20), (4, 4, 24, 16)])
+def test_general_kernel_codes_match_dense_products(gpu_ctx, tx, rx, m, r):
+    """The general kernel keeps the 2-bit codes of a quantised A in shared memory (products without global reads of
+    A, I + A A' by popcount arithmetic); with the option "fast" off it runs the dense products on the same instance.
+    Same algorithm, different rounding: the states agree to 1e-11 after 6 iterations, the bookkeeping exactly."""
+    import twoace_b200 as tw
+    from twoace_b200 import solvers as sv
+    A, B, _ = _synthetic_case(tx, rx, m, 40 + tx + r)
+    A, B, _, _ = admm._preprocess(A, B, 1e-8)
+    n = tx * rx
+    X0 = admm.spectral_initialize(A, B, r)
+    p = tw.Params.default(maxiter=6, tol_rel=0.0, tol_abs=0.0)
+    _, _, Sc, Wc = sv.infer_admm_batch([A], [B], [X0], r > 1, False, tx, rx, p, ctx=gpu_ctx)
+    gpu_ctx.set_option("fast", 0)
+    try:
+        _, _, Sd, Wd = sv.infer_admm_batch([A], [B], [X0], r > 1, False, tx, rx, p, ctx=gpu_ctx)
+    finally:
+        gpu_ctx.set_option("fast", 1)
+    for k in ("X", "Y", "Z"):
+        assert rel(Sc[0][k], Sd[0][k]) < 1e-11 or np.linalg.norm(Sd[0][k]) < 1e-12
+    assert np.array_equal(Wc[0][2:7], Wd[0][2:7])       # iterations, best iteration / column, mu bumps, converged
+
+
 @pytest.mark.parametrize("tx,rx,m", [(8, 8, 48), (4, 4, 40)])
 def test_full_solve_other_antenna_counts(gpu_ctx, tx, rx, m):
     """inferLowRankV4 end to end (default tolerances) away from 16 x 16: same flags, quality and CSI."""

@@ -249,7 +249,9 @@ int twoace_synth_batch(twoace_ctx* ctx, int mem, int nb, const twoace_synth_para
                        int32_t* cb_rows, int32_t* train_idx, double* B, double* vecH, double* angles);
 
 /* Execution options.  "fast" (default 1): run eligible InferADMM launches (16x16, quantised 4-phase A,
- * r in {20,1}, m <= 256, V4 ArgMinZ) on the shared-memory cluster kernel instead of the general one;
+ * r in {20,1}, m <= 1024, V4 or nuclear ArgMinZ) on the shared-memory cluster kernels instead of the general one, and let
+ * the general kernel keep the 2-bit codes of a quantised A in shared memory (any n divisible by 16); 0 = general
+ * kernel with dense products for everything;
  * "fast_cs" (2 or 4, default 2): cluster size of the r = 20 stages; "chunk": instances per internal pass;
  * "dedup_nuclear_rerun" (default 0): inferLowRank_Nuclear.m:69-70 reruns the train solve with use_rank_one = true,
  * a flag its ArgMinZ (:411-419) never reads, so the rerun reproduces the first run bit for bit; 1 = do not

@@ -207,6 +207,7 @@ __device__ __forceinline__ void gemm_tpo_t(int nout, int K, int r, MatF mat, OpF
 template <int RC, class MatF, class OpF, class StoreF>
 __device__ __forceinline__ void gemm_tpo_2r(int nout, int K, int r, MatF mat, OpF opnd, StoreF store, cd* tile,
                                             cd* ksred) {
+  constexpr int QT2 = QT * RCH / RC;     // the tile buffer holds QT x RCH elements: longer tiles, fewer fills and barriers
   const int tid = threadIdx.x;
   for (int c0 = 0; c0 < r; c0 += RC) {
     const int rc = min(RC, r - c0);
@@ -219,11 +220,11 @@ __device__ __forceinline__ void gemm_tpo_2r(int nout, int K, int r, MatF mat, Op
       cd acc0[RC], acc1[RC];
 #pragma unroll
       for (int j = 0; j < RC; ++j) { acc0[j] = cmk(0.0, 0.0); acc1[j] = cmk(0.0, 0.0); }
-      for (int q0 = 0; q0 < K; q0 += QT) {
-        const int ql = min(QT, K - q0);
+      for (int q0 = 0; q0 < K; q0 += QT2) {
+        const int ql = min(QT2, K - q0);
         __syncthreads();
-        for (int idx = tid; idx < QT * RC; idx += NT) {
-          int j = idx / QT, q = idx - j * QT;
+        for (int idx = tid; idx < QT2 * RC; idx += NT) {
+          int j = idx / QT2, q = idx - j * QT2;
           tile[q * RC + j] = (q < ql && j < rc) ? opnd(q0 + q, c0 + j) : cmk(0.0, 0.0);
         }
         __syncthreads();

@@ -229,3 +229,30 @@ def test_minl2_oracle_properties():
     assert q > 0.9
     c = np.vdot(Xh, x) / np.vdot(Xh, Xh)
     assert np.linalg.norm(x - c * Xh) / np.linalg.norm(x) < 1e-2
+
+
+def test_two_bit_code_gram_identity():
+    """The identity behind the general kernel's build of I + A A' from 2-bit codes (csrc/admm_stage.cuh): with
+    A(i,k) = c * j^code(i,k), (A A')(i,j) = c^2 * sum_k j^((code_i - code_j) mod 4); per 32-bit word of 16 codes the
+    differences come from one 2-bit-field subtraction and their counts from three popcounts."""
+    rng = np.random.default_rng(12)
+    m, n = 9, 64
+    codes = rng.integers(0, 4, (m, n))
+    A = 0.125 * (1j ** codes)
+    words = np.zeros((m, n // 16), dtype=np.uint64)
+    for k in range(n):
+        words[:, k // 16] |= codes[:, k].astype(np.uint64) << np.uint64(2 * (k % 16))
+    HB, LB, M32 = 0xAAAAAAAA, 0x55555555, 0xFFFFFFFF
+    G = np.zeros((m, m), dtype=np.complex128)
+    for i in range(m):
+        for j in range(m):
+            re = im = 0
+            for w in range(n // 16):
+                x, y = int(words[i, w]), int(words[j, w])
+                d = ((((x | HB) - (y & LB)) & M32) ^ ((x ^ (~y & M32)) & HB)) & M32
+                hi, lo = (d >> 1) & LB, d & LB
+                n3, n2, n1 = bin(hi & lo).count("1"), bin(hi & ~lo & M32).count("1"), bin(lo & ~hi & M32).count("1")
+                re += 16 - n1 - 2 * n2 - n3
+                im += n1 - n3
+            G[i, j] = 0.125 ** 2 * (re + 1j * im)
+    assert np.array_equal(G, A @ A.conj().T)          # powers of two and small integers: exact on both sides

@@ -32,6 +32,17 @@ def test_header_symbols_are_exported(built):
     assert sorted(built.lib.EXPORTS) == names, "lib.py EXPORTS out of sync with twoace.h"
 
 
+def test_build_recipe_compiles_every_translation_unit():
+    """Every .cu file under csrc/ is on the nvcc command line of __graft_entry__.build() (a kernel that lives in its
+    own translation unit and is left out would only show up as an unresolved symbol at load time)."""
+    import inspect
+    import __graft_entry__ as g
+    recipe = inspect.getsource(g.build)
+    csrc = os.path.join(ROOT, "2ace-mmwave-channel-estimation_b200", "csrc")
+    units = sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+    assert units and all(f'"{u}"' in recipe for u in units), units
+
+
 def test_default_params_match_reference_defaults(built):
     lib = built.lib.load()
     p = built.lib.Params()
